@@ -1,0 +1,160 @@
+/*
+ * sp_b200.h -- C ABI of the B200-native stair-perception segmentation front-end (libsp_b200.so).
+ *
+ * The reference has no FFI layer: its seam is the C++ class StairDetection in libstairperception.so
+ *   ctor     StairDetection(ParameterDef)            /root/reference/modules/stairperception/StairPerception.hpp:144-184
+ *   process  bool process(cloud_in, show_mode, stair, vector_plane_sorted, cloud_show, normal_show)
+ *                                                    /root/reference/modules/stairperception/StairPerception.hpp:127-132
+ *                                                    /root/reference/modules/stairperception/StairPerception.cpp:5-214
+ * and, upstream of it, the levelling free functions  /root/reference/test/reader.cpp:228-324.
+ * Each entry point below names the reference interface it replaces.  Plain pointers and sizes only; no
+ * torch / PCL / Eigen types; never throws; status < 0 = argument or CUDA error (text via sp_last_error).
+ * "No stair" / "too few points" are results, not errors (reference: silent `return false`,
+ * StairPerception.cpp:24, :56).
+ *
+ * There is NO CPU path in this library: every entry point that computes runs CUDA kernels on the
+ * context's device and fails with SP_ERR_CUDA when no device is available.
+ */
+#ifndef SP_B200_H_
+#define SP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_OK 0
+#define SP_ERR_ARG (-1)
+#define SP_ERR_CUDA (-2)
+#define SP_ERR_CAPACITY (-3)
+
+#define SP_MAX_PLANES 64        /* per frame, after merge (H + V) */
+
+/* ShowModeDef, /root/reference/include/common.h:79-92 */
+enum sp_show_mode {
+    SP_SHOW_ORIGINAL = 0, SP_SHOW_RANGE_LIMITED, SP_SHOW_VOXEL, SP_SHOW_NOLEG, SP_SHOW_HORIZONTAL_CLOUD,
+    SP_SHOW_VERTICAL_CLOUD, SP_SHOW_SEG_HORIZONTAL_PLANE, SP_SHOW_SEG_VERTICAL_PLANE,
+    SP_SHOW_MERGE_HORIZONTAL_PLANE, SP_SHOW_MERGE_VERTICAL_PLANE, SP_SHOW_STAIR
+};
+
+/* ParameterDef, /root/reference/include/common.h:94-131 -- same 35 fields, same order, same types.
+ * The library narrows them to float exactly where the StairDetection ctor does (StairPerception.hpp:146-180). */
+typedef struct sp_params {
+    double x_min, x_max, y_min, y_max, z_min, z_max;
+    int normal_compute_points;
+    double voxel_x, voxel_y, voxel_z;
+    double parallel_angle_diff, perpendicular_angle_diff;
+    double cluster_tolerance;
+    int min_cluster_size, max_cluster_size;
+    double seg_threshold;
+    int seg_max_iters, seg_rest_point;
+    double seg_plane_angle_diff;
+    double merge_threshold, merge_angle_diff;
+    int min_num_points;
+    double min_length, max_length, min_width, max_width;
+    double max_g_height, counter_max_distance;
+    double min_height, max_height;
+    double vertical_angle_diff, mcv_angle_diff, center_vector_angle_diff, vertical_plane_angle_diff;
+    double noleg_distance;
+} sp_params;
+
+/* Hand-off record per plane = every field of `Plane` (/root/reference/include/common.h:150-185) except
+ * the bulk cloud, which stays on the device as an index list (sp_copy_plane_points). */
+typedef struct sp_plane_record {
+    int32_t type;            /* Plane::Type: 0 vertical, 1 horizontal */
+    int32_t ptype;           /* Plane::Ptype; sortPlanesByXValues sets 3 = others (StairPerception.cpp:1448) */
+    int32_t count;           /* points in the plane cloud */
+    int32_t first;           /* offset of this plane's points inside the frame's plane point list */
+    float coef[4];           /* a, b, c, d */
+    float center[3];
+    float pcenter[3];
+    float evec[9];           /* evec[3*j+k] = component k of eigen_vectors[j] */
+    float eval[3];
+    float pmin[3], pmax[3];  /* min[a], max[a] */
+    float pt_min[3][3], pt_max[3][3];   /* xyz of points_min[a] / points_max[a]; NaN when never set */
+    int32_t idx_min[3], idx_max[3];     /* pixel index of those points, -1 when never set */
+} sp_plane_record;
+
+/* Fixed-size per-frame result (what a multi-GPU run gathers). */
+typedef struct sp_frame_result {
+    int32_t status;          /* 0 = ran to the end; 1 = stopped at the "<100 points after crop" guard
+                                (StairPerception.cpp:56); 2 = voxel-grid overflow guard
+                                (voxel_grid_indices.hpp:295-303); bit 8 set = a device-side capacity was hit */
+    int32_t n_valid;         /* rgb != 0 (remove_nan_points, StairPerception.cpp:338) and finite */
+    int32_t n_crop;          /* after passThroughCloudANDNormal */
+    int32_t n_voxel;         /* occupied voxels */
+    int32_t n_nonan;         /* after removeNANNormalPoints */
+    int32_t n_noleg;         /* after removeClosetPoints */
+    int32_t n_h, n_v;        /* extractPerpendicularPlanePoints */
+    int32_t n_clusters_h, n_clusters_v;   /* clusters within [min_cluster_size, max_cluster_size] */
+    int32_t n_seg_h, n_seg_v;             /* planes out of segmentHorizontalPlanes / segmentVerticalPlanes */
+    int32_t n_planes_h, n_planes_v;       /* after mergeSeperatedPlanes */
+    int32_t n_planes;                     /* records filled below (sorted by sortPlanesByXValues) */
+    int32_t n_plane_points;               /* total length of the frame's plane point list */
+    sp_plane_record planes[SP_MAX_PLANES];
+} sp_frame_result;
+
+typedef struct sp_ctx sp_ctx;
+
+/* Replaces StairDetection::StairDetection(ParameterDef) (StairPerception.hpp:144).  Because the reference
+ * constructs the object once per frame (test/processor.cpp:156), all device state lives in this context
+ * instead: streams, workspaces for `max_batch` frames of width x height points.  device = CUDA ordinal. */
+int sp_create(const sp_params *params, int device, int width, int height, int max_batch, sp_ctx **out);
+void sp_destroy(sp_ctx *ctx);
+const char *sp_last_error(const sp_ctx *ctx);   /* ctx may be NULL: returns the last create error */
+
+/* Replaces DProcessor::update_parameters -> new StairDetection(parameters) (test/processor.cpp:102-109,156). */
+int sp_set_params(sp_ctx *ctx, const sp_params *params);
+
+/* Replaces computeRotationMatrix (test/reader.cpp:228-249 Euler, :251-271 quaternion).  Host-side, 9 floats,
+ * row-major R = m3 * R_imu * m1. */
+void sp_rotation_from_euler(float pitch_deg, float roll_deg, float yaw_deg, float *R9);
+void sp_rotation_from_quat(float w, float x, float y, float z, float *R9);
+
+/* Replaces rotationCloudPoints (test/reader.cpp:273-324) + StairDetection::process up to the hand-off to
+ * stairModel (StairPerception.cpp:5-188) for `nframes` independent frames.
+ *   xyzrgba : nframes x (width*height) x 16 B records {float x, y, z; uint32 rgba} (the PCD record layout)
+ *   R9      : nframes x 9 row-major levelling rotations, or NULL = already levelled (files mode, reader.cpp:493)
+ *   results : nframes records, caller-allocated
+ * sp_process_frames takes HOST pointers (copies inside); sp_process_frames_device takes DEVICE pointers to
+ * inputs already resident in HBM and still writes `results` to host memory.  nframes may exceed max_batch:
+ * the call loops over chunks.  show_mode: SP_SHOW_* (SP_SHOW_ORIGINAL does no work, StairPerception.cpp:24;
+ * the other taps stop the pipeline where process() returns early). */
+int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode,
+                      sp_frame_result *results);
+int sp_process_frames_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int show_mode,
+                             sp_frame_result *results);
+
+/* Stage taps of the LAST chunk processed (the ShowModeDef taps of process(), StairPerception.cpp:49-176, plus
+ * the intermediate arrays the parity tests compare).  `frame` indexes the last chunk.  Names:
+ *   "xyz" (N x 3 float, levelled+masked)  "normals" (N x 3 float)  "minmax" (6 float)  "voxel_key" (N u32)
+ *   "voxel_idx" "h_idx" "v_idx" (int32 pixel indices)   "h_root" "v_root" (int32 per H/V point: smallest
+ *   member position of its cluster)   "h_seg_coef" "v_seg_coef" (P x 4 float)  "h_seg_count" "v_seg_count"
+ *   "h_seg_idx" "v_seg_idx" (int32 pixel indices, planes concatenated)   "h_hyp" "v_hyp" (int32 x 4 per scored
+ *   hypothesis: call id, i0, i1, i2)   "plane_idx" (int32 pixel indices of the final planes, concatenated)
+ * Returns bytes (sp_tap_bytes), bytes copied (sp_tap_copy) or <0 on error / unknown name. */
+int64_t sp_tap_bytes(sp_ctx *ctx, int frame, const char *name);
+int64_t sp_tap_copy(sp_ctx *ctx, int frame, const char *name, void *dst, int64_t cap);
+
+/* Replaces reading Plane::cloud (common.h:152): xyz (3 floats / point) and pixel indices of plane `plane`
+ * of frame `frame` of the last chunk, in the reference's point order.  Either output may be NULL. */
+int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t *pixel_idx, int cap);
+
+/* Timing of the last chunk: CUDA-event milliseconds per stage; returns number of stages written. */
+int sp_stage_ms(sp_ctx *ctx, float *out, int cap);
+const char *sp_stage_name(int i);
+/* number of kernels this library launched since sp_create (its own + CUB) */
+int64_t sp_launch_count(const sp_ctx *ctx);
+
+/* Run only one stage on device-resident inputs (bench / profiling of a single kernel family).
+ * stage: 0 = ingest+normals, 1 = voxel (key+sort+pick), 2 = whole pipeline w/o D2H. */
+int sp_run_stage_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int stage);
+
+/* CUDA stream handle (cudaStream_t) the context launches on, for callers that time with events. */
+void *sp_stream(sp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SP_B200_H_ */
