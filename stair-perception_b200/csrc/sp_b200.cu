@@ -1,0 +1,559 @@
+/*
+ * sp_b200.cu -- host side of libsp_b200.so: context, workspaces, the per-chunk launch sequence, stage taps.
+ * C ABI declared in include/sp_b200.h.  No CPU compute path: every processing entry point launches CUDA kernels.
+ */
+#include "sp_common.cuh"
+#include "sp_front.cuh"
+#include "sp_seg.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_create_error;
+
+enum { STG_NORMALS = 0, STG_VOXEL, STG_CLUSTER, STG_RANSAC, STG_PLANES, STG_COUNT };
+const char *kStageNames[STG_COUNT] = { "ingest_normals", "voxel", "cluster", "ransac", "merge_stats_finalize" };
+
+/* pcl::deg2rad(float) */
+inline float deg2radf(float a) { return a * 0.017453293f; }
+
+/* monotone bijection float <-> int32 */
+inline int32_t f2ord(float f) { int32_t b; memcpy(&b, &f, 4); return b >= 0 ? b : (int32_t)(b ^ 0x7fffffff); }
+inline float ord2f(int32_t o) { int32_t b = o >= 0 ? o : (int32_t)(o ^ 0x7fffffff); float f; memcpy(&f, &b, 4); return f; }
+
+/* a8 (extractPerpendicularPlanePoints, StairPerception.cpp:696-707) compares angle = acos((double)nx) with two
+ * thresholds.  acos is monotone, so each comparison is a half-line in nx; the end points are found once, here,
+ * by bisection over the float ordering using the host libm the reference itself would call.  The kernel then
+ * classifies with float compares only and gives the same answer as the reference expression for every float. */
+template <class Pred> float lowest_true(Pred pred, float lo, float hi)     /* pred monotone: false...true on [lo,hi] */
+{
+    if (!pred(hi)) return INFINITY;
+    if (pred(lo)) return lo;
+    int32_t a = f2ord(lo), b = f2ord(hi);                                  /* pred(a) false, pred(b) true */
+    while ((int64_t)b - a > 1) { const int32_t m = (int32_t)(((int64_t)a + b) / 2); if (pred(ord2f(m))) b = m; else a = m; }
+    return ord2f(b);
+}
+template <class Pred> float highest_true(Pred pred, float lo, float hi)    /* pred monotone: true...false on [lo,hi] */
+{
+    if (!pred(lo)) return -INFINITY;
+    if (pred(hi)) return hi;
+    int32_t a = f2ord(lo), b = f2ord(hi);                                  /* pred(a) true, pred(b) false */
+    while ((int64_t)b - a > 1) { const int32_t m = (int32_t)(((int64_t)a + b) / 2); if (pred(ord2f(m))) a = m; else b = m; }
+    return ord2f(a);
+}
+
+void make_consts(const sp_params &p, SpConst &c)
+{
+    c.x0 = (float)p.x_min; c.x1 = (float)p.x_max; c.y0 = (float)p.y_min; c.y1 = (float)p.y_max; c.z0 = (float)p.z_min; c.z1 = (float)p.z_max;
+    c.ivx = 1.0f / (float)p.voxel_x; c.ivy = 1.0f / (float)p.voxel_y; c.ivz = 1.0f / (float)p.voxel_z;
+    const float th = (float)p.noleg_distance;
+    c.noleg_th2 = th * th;
+    const double t1 = (double)deg2radf((float)p.parallel_angle_diff), t2 = (double)deg2radf((float)p.perpendicular_angle_diff);
+    c.h_ge = lowest_true([&](float v) { return acos((double)v) < t1; }, -1.0f, 1.0f);
+    c.h_le = highest_true([&](float v) { return M_PI - acos((double)v) < t1; }, -1.0f, 1.0f);
+    auto vp = [&](float v) { return fabs(acos((double)v) - M_PI / 2) < t2; };
+    c.v_lo = lowest_true(vp, -1.0f, 0.0f);
+    c.v_hi = highest_true(vp, 0.0f, 1.0f);
+    if (!vp(0.0f)) { c.v_lo = INFINITY; c.v_hi = -INFINITY; }
+    const double radius = (double)(float)p.cluster_tolerance;
+    c.r2 = (float)(radius * radius);
+    c.cell = (float)radius * 1.0001f;
+    c.min_c = p.min_cluster_size; c.max_c = p.max_cluster_size;
+    c.seg_thr = (float)p.seg_threshold;
+    c.sin_angle = fabs(sin((double)deg2radf((float)p.seg_plane_angle_diff)));
+    c.max_iters = p.seg_max_iters;
+    c.rest = std::max(3, p.seg_rest_point);       /* < 3 makes the reference's extract loop spin forever */
+    c.merge_ath = (double)deg2radf((float)p.merge_angle_diff);
+    c.merge_thr = (float)p.merge_threshold;
+    c.log_prob = det_log(1.0 - 0.99);
+}
+
+/* glibc rand(): TYPE_3 additive feedback generator (stdlib/random_r.c), default seed 1 */
+void glibc_rand_stream(int n, int *out)
+{
+    std::vector<int32_t> r(344 + n);
+    r[0] = 1;
+    for (int i = 1; i < 31; ++i) {
+        const int64_t hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        int64_t w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = (int32_t)w;
+    }
+    for (int i = 31; i < 34; ++i) r[i] = r[i - 31];
+    for (int i = 34; i < 344 + n; ++i) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
+    for (int i = 0; i < n; ++i) out[i] = (int)(((uint32_t)r[344 + i]) >> 1);
+}
+
+} // namespace
+
+struct sp_ctx {
+    int device = 0, W = 0, H = 0, N = 0, B = 0;
+    sp_params params;
+    SpDev d;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::vector<void *> allocs;
+    void *cub_temp = nullptr; size_t cub_bytes = 0;
+    float4 *d_in[2] = { nullptr, nullptr }; float *d_R[2] = { nullptr, nullptr };
+    int *d_order = nullptr;
+    sp_frame_result *h_results = nullptr;     /* pinned */
+    cudaEvent_t ev[STG_COUNT + 1];
+    cudaEvent_t ev_in[2], ev_done[2];
+    float stage_ms[STG_COUNT];
+    int last_nB = 0;
+    int64_t launches = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SP_ERR_CUDA; } } while (0)
+
+template <class T> cudaError_t dalloc(sp_ctx *ctx, T **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) { ctx->allocs.push_back(q); *p = (T *)q; }
+    return e;
+}
+
+int frame_bits(int B) { int b = 0; while ((1 << b) < B) ++b; return b; }
+
+/* the per-chunk launch sequence; `upto` = last stage group to run */
+int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int show_mode, int only_stage)
+{
+    SpDev d = ctx->d;
+    d.in = d_in; d.R = d_R; d.B = nB;
+    cudaStream_t st = ctx->stream;
+    const int N = ctx->N;
+    ctx->last_nB = nB;
+    const bool all = only_stage < 0 || only_stage == 2;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    if (all || only_stage == 0) {
+        k_init_frames<<<(nB * SP_NCOUNT + 255) / 256, 256, 0, st>>>(d, nB);
+        dim3 g((ctx->W + K1_TW - 1) / K1_TW, (ctx->H + K1_TH - 1) / K1_TH, nB);
+        k_ingest_normals<<<g, K1_THREADS, sizeof(K1Smem), st>>>(d);
+        ctx->launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
+    if (want_voxel) {
+        k_frame_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, nB);
+        k_voxel_key<<<dim3(std::min(d.nblk, 148), nB), 256, 0, st>>>(d);
+        size_t tb = ctx->cub_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)nB * N, 0, 32 + frame_bits(nB), st));
+        k_voxel_pick<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        k_scan_blocks<<<nB, 256, 0, st>>>(d);
+        k_scatter_lists<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        ctx->launches += 5 + 2 + (32 + frame_bits(nB) + 7) / 8;
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+    const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
+    if (want_seg) {
+        CK(cudaMemsetAsync(d.head, 0xff, sizeof(int) * ((size_t)2 * nB << SP_HASH_BITS), st));
+        k_cl_build<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_union<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_flatten<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_rank<<<2 * nB, 256, 0, st>>>(d);
+        ctx->launches += 4;
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    if (want_seg) {
+        k_clear_planes<<<(2 * nB * SP_PSEG + 255) / 256, 256, 0, st>>>(d, 2 * nB);
+        k_ransac<<<dim3(SP_CMAX, 2 * nB), 256, 0, st>>>(d);
+        ctx->launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[4], st));
+    if (all) {
+        if (want_seg) {
+            k_merge<<<(nB + 31) / 32, 32, 0, st>>>(d, nB);
+            ctx->launches += 1;
+            if (show_mode >= SP_SHOW_STAIR) {
+                k_plane_stats<<<dim3(SP_PSEG, 2 * nB), 256, 0, st>>>(d);
+                ctx->launches += 1;
+            }
+        }
+        k_finalize<<<(nB + 63) / 64, 64, 0, st>>>(d, nB, ctx->d_order, (want_seg && show_mode >= SP_SHOW_STAIR) ? 1 : 0);
+        k_gather_plane_points<<<dim3(SP_MAX_PLANES, nB), 256, 0, st>>>(d, ctx->d_order);
+        ctx->launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaGetLastError());
+    return SP_OK;
+}
+
+int collect_times(sp_ctx *ctx)
+{
+    for (int i = 0; i < STG_COUNT; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) ms = 0.f;
+        ctx->stage_ms[i] = ms;
+    }
+    (void)cudaGetLastError();
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *sp_last_error(const sp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sp_set_params(sp_ctx *ctx, const sp_params *params)
+{
+    if (!ctx || !params) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!(params->voxel_x > 0) || !(params->voxel_y > 0) || !(params->voxel_z > 0) || !(params->cluster_tolerance > 0) ||
+        params->seg_max_iters < 0) { ctx->err = "invalid parameters"; return SP_ERR_ARG; }
+    ctx->params = *params;
+    make_consts(*params, ctx->d.c);
+    return SP_OK;
+}
+
+int sp_create(const sp_params *params, int device, int width, int height, int max_batch, sp_ctx **out)
+{
+    if (!params || !out || width < 1 || height < 1 || max_batch < 1 || max_batch > 4096) { g_create_error = "bad argument"; return SP_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
+        return SP_ERR_CUDA;
+    }
+    sp_ctx *ctx = new sp_ctx();
+    ctx->device = device; ctx->W = width; ctx->H = height; ctx->N = width * height; ctx->B = max_batch;
+    memset(&ctx->d, 0, sizeof(ctx->d));
+    memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
+    auto fail = [&](const char *what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        sp_destroy(ctx);
+        return SP_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if (sp_set_params(ctx, params) != SP_OK) { g_create_error = ctx->err; sp_destroy(ctx); return SP_ERR_ARG; }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (int i = 0; i <= STG_COUNT; ++i) if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    }
+    SpDev &d = ctx->d;
+    const size_t B = max_batch, N = ctx->N, BN = B * N, S = 2 * B;
+    d.W = width; d.H = height; d.N = ctx->N; d.B = max_batch;
+    d.nblk = (int)((N + 1023) / 1024);
+#define DA(ptr, n) if ((e = dalloc(ctx, &(ptr), (n))) != cudaSuccess) return fail("cudaMalloc " #ptr, e)
+    DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
+    DA(d.x, BN); DA(d.y, BN); DA(d.z, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
+    DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
+    DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
+    DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
+    DA(d.pts, S * N); DA(d.seg_n, S); DA(d.head, S << SP_HASH_BITS);
+    DA(d.next, S * N); DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
+    DA(d.n_clusters, S); DA(d.n_cand, S);
+    DA(d.cand_root, S * SP_CMAX); DA(d.cand_size, S * SP_CMAX); DA(d.cand_off, S * SP_CMAX); DA(d.cand_slot, S * SP_CMAX);
+    DA(d.wx, S * N); DA(d.wy, S * N); DA(d.wz, S * N); DA(d.wpix, S * N); DA(d.plane_pts, S * N);
+    DA(d.seg_planes, S * SP_PSEG); DA(d.logs, S * SP_LOGCAP * 10); DA(d.log_n, S);
+    DA(d.n_seg, S); DA(d.chunks, S * SP_PSEG); DA(d.chunk_next, S * SP_PSEG); DA(d.merged, S * SP_PSEG); DA(d.n_merged, S);
+    DA(d.info, S * SP_PSEG); DA(d.results, B); DA(d.plane_idx, BN); DA(ctx->d_order, B * SP_MAX_PLANES);
+    int *mt = nullptr, *rnd = nullptr;
+    DA(mt, SP_MT_LEN); DA(rnd, SP_RAND_LEN);
+#undef DA
+    {
+        std::vector<int> h(SP_MT_LEN);
+        std::mt19937 rng(12345u);                               /* boost::mt19937 seeded 12345 (sac_model.h) */
+        for (int i = 0; i < SP_MT_LEN; ++i) h[i] = (int)(rng() >> 1);   /* boost::uniform_int<>(0, INT_MAX) */
+        if ((e = cudaMemcpy(mt, h.data(), sizeof(int) * SP_MT_LEN, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy mt", e);
+        std::vector<int> r(SP_RAND_LEN);
+        glibc_rand_stream(SP_RAND_LEN, r.data());
+        if ((e = cudaMemcpy(rnd, r.data(), sizeof(int) * SP_RAND_LEN, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy rnd", e);
+        d.mt = mt; d.rnd = rnd;
+    }
+    {
+        size_t tb = 0;
+        e = cub::DeviceRadixSort::SortPairs(nullptr, tb, d.key_a, d.key_b, d.val_a, d.val_b, BN, 0, 32 + frame_bits(max_batch), ctx->stream);
+        if (e != cudaSuccess) return fail("cub temp size", e);
+        ctx->cub_bytes = tb;
+        void *q = nullptr;
+        if ((e = cudaMalloc(&q, std::max<size_t>(tb, 16))) != cudaSuccess) return fail("cudaMalloc cub", e);
+        ctx->allocs.push_back(q); ctx->cub_temp = q;
+    }
+    if ((e = cudaMallocHost((void **)&ctx->h_results, sizeof(sp_frame_result) * B)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaFuncSetAttribute(k_ingest_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    *out = ctx;
+    return SP_OK;
+}
+
+void sp_destroy(sp_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->h_results) cudaFreeHost(ctx->h_results);
+    for (int i = 0; i <= STG_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+void sp_rotation_from_euler(float pitch, float roll, float yaw, float *R9)
+{
+    /* m2 = Rx(roll) * Ry(pitch) * Rz(yaw); angles = v / 180.0 * M_PI in double, narrowed (reader.cpp:240-242) */
+    const float ar = (float)(roll / 180.0 * M_PI), ap = (float)(pitch / 180.0 * M_PI), ay = (float)(yaw / 180.0 * M_PI);
+    const float cr = cosf(ar), sr = sinf(ar), cp = cosf(ap), sp = sinf(ap), cy = cosf(ay), sy = sinf(ay);
+    const float Rx[9] = { 1, 0, 0, 0, cr, -sr, 0, sr, cr }, Ry[9] = { cp, 0, sp, 0, 1, 0, -sp, 0, cp }, Rz[9] = { cy, -sy, 0, sy, cy, 0, 0, 0, 1 };
+    auto mul = [](const float *A, const float *Bm, float *C) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * Bm[j] + A[3 * i + 1] * Bm[3 + j] + A[3 * i + 2] * Bm[6 + j];
+    };
+    const float m1[9] = { 0, 0, 1, -1, 0, 0, 0, -1, 0 }, m3[9] = { 0, 0, -1, 1, 0, 0, 0, -1, 0 };
+    float t[9], m2[9], u[9];
+    mul(Rx, Ry, t); mul(t, Rz, m2); mul(m3, m2, u); mul(u, m1, R9);
+}
+
+void sp_rotation_from_quat(float w, float x, float y, float z, float *R9)
+{
+    const float n = sqrtf(w * w + x * x + y * y + z * z);
+    w /= n; x /= n; y /= n; z /= n;
+    const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z, twx = tx * w, twy = ty * w, twz = tz * w,
+                txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const float m2[9] = { 1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1.f - (txx + tyy) };
+    auto mul = [](const float *A, const float *Bm, float *C) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * Bm[j] + A[3 * i + 1] * Bm[3 + j] + A[3 * i + 2] * Bm[6 + j];
+    };
+    const float m1[9] = { 0, 0, 1, -1, 0, 0, 0, -1, 0 }, m3[9] = { 0, 0, -1, 1, 0, 0, 0, -1, 0 };
+    float u[9];
+    mul(m3, m2, u); mul(u, m1, R9);
+}
+
+static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results, bool host_in)
+{
+    if (!ctx || !xyzrgba || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR || (!results && nframes > 0)) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const size_t fb = (size_t)ctx->N * 16;
+    if (show_mode == SP_SHOW_ORIGINAL) { memset(results, 0, sizeof(sp_frame_result) * (size_t)nframes); return SP_OK; }
+    int buf = 0;
+    /* chunk loop; with host input the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i */
+    const int nchunks = (nframes + ctx->B - 1) / ctx->B;
+    auto issue_copy = [&](int ci, int b) -> int {
+        const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CK(cudaMemcpyAsync(ctx->d_in[b], (const uint8_t *)xyzrgba + fb * f0, fb * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (R9) CK(cudaMemcpyAsync(ctx->d_R[b], R9 + 9 * (size_t)f0, sizeof(float) * 9 * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+        return SP_OK;
+    };
+    if (host_in && nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
+        const float4 *din; const float *dR;
+        if (host_in) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
+            din = ctx->d_in[buf]; dR = R9 ? ctx->d_R[buf] : nullptr;
+            if (ci + 1 < nchunks) { const int rc = issue_copy(ci + 1, buf ^ 1); if (rc) return rc; }
+        } else {
+            din = (const float4 *)((const uint8_t *)xyzrgba + fb * f0); dR = R9 ? R9 + 9 * (size_t)f0 : nullptr;
+        }
+        CK(cudaMemsetAsync(ctx->d.results, 0, sizeof(sp_frame_result) * nB, ctx->stream));
+        const int rc = run_chunk(ctx, din, dR, nB, show_mode, -1);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_results, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(results + f0, ctx->h_results, sizeof(sp_frame_result) * nB);
+        buf ^= 1;
+    }
+    collect_times(ctx);
+    return SP_OK;
+}
+
+int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results)
+{
+    return process_impl(ctx, xyzrgba, R9, nframes, show_mode, results, true);
+}
+
+int sp_process_frames_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int show_mode, sp_frame_result *results)
+{
+    return process_impl(ctx, d_xyzrgba, d_R9, nframes, show_mode, results, false);
+}
+
+int sp_run_stage_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int stage)
+{
+    if (!ctx || !d_xyzrgba || nframes < 1 || nframes > ctx->B || stage < 0 || stage > 2) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    return run_chunk(ctx, (const float4 *)d_xyzrgba, d_R9, nframes, SP_SHOW_STAIR, stage);
+}
+
+void *sp_stream(sp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int sp_stage_ms(sp_ctx *ctx, float *out, int cap)
+{
+    if (!ctx || !out) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    collect_times(ctx);
+    const int n = std::min(cap, (int)STG_COUNT);
+    for (int i = 0; i < n; ++i) out[i] = ctx->stage_ms[i];
+    return n;
+}
+const char *sp_stage_name(int i) { return (i >= 0 && i < STG_COUNT) ? kStageNames[i] : ""; }
+int64_t sp_launch_count(const sp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+/* ------------------------------------------------------------------------------------------------ taps */
+static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vector<uint8_t> &out)
+{
+    if (frame < 0 || frame >= ctx->last_nB) { ctx->err = "frame out of range"; return SP_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const SpDev &d = ctx->d;
+    const size_t N = ctx->N, f = frame;
+    auto d2h = [&](void *dst, const void *src, size_t bytes) { return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
+    std::vector<int> counts(SP_NCOUNT);
+    CK(d2h(counts.data(), d.counts + f * SP_NCOUNT, sizeof(int) * SP_NCOUNT));
+    auto put_i = [&](const std::vector<int> &v) { out.resize(v.size() * 4); if (!v.empty()) memcpy(out.data(), v.data(), out.size()); };
+    if (name == "xyz" || name == "normals") {
+        std::vector<float> a(N), b(N), c(N);
+        const bool nrm = name == "normals";
+        CK(d2h(a.data(), (nrm ? d.nx : d.x) + f * N, N * 4)); CK(d2h(b.data(), (nrm ? d.ny : d.y) + f * N, N * 4)); CK(d2h(c.data(), (nrm ? d.nz : d.z) + f * N, N * 4));
+        out.resize(N * 12);
+        float *o = (float *)out.data();
+        for (size_t i = 0; i < N; ++i) { o[3 * i] = a[i]; o[3 * i + 1] = b[i]; o[3 * i + 2] = c[i]; }
+        return SP_OK;
+    }
+    if (name == "counts") { put_i(counts); return SP_OK; }
+    if (name == "minmax") {
+        int mm[8]; CK(d2h(mm, d.mm + f * 8, sizeof(mm)));
+        out.resize(24); float *o = (float *)out.data();
+        for (int k = 0; k < 6; ++k) o[k] = ord2f(mm[k]);
+        return SP_OK;
+    }
+    if (name == "voxel_key") {
+        std::vector<unsigned long long> k(N); CK(d2h(k.data(), d.key_a + f * N, N * 8));
+        out.resize(N * 4); uint32_t *o = (uint32_t *)out.data();
+        for (size_t i = 0; i < N; ++i) o[i] = (uint32_t)k[i];
+        return SP_OK;
+    }
+    if (name == "voxel_idx" || name == "nonan_idx" || name == "noleg_idx" || name == "voxel_code") {
+        const int nv = counts[3];
+        std::vector<int> idx(nv); std::vector<unsigned char> code(nv);
+        CK(d2h(idx.data(), d.voxel_idx + f * N, (size_t)nv * 4)); CK(d2h(code.data(), d.voxel_code + f * N, (size_t)nv));
+        if (name == "voxel_code") { out.assign(code.begin(), code.end()); return SP_OK; }
+        const int need = name == "voxel_idx" ? SPC_HEAD : (name == "nonan_idx" ? SPC_NONAN : SPC_NOLEG);
+        std::vector<int> v;
+        for (int i = 0; i < nv; ++i) if (code[i] & need) v.push_back(idx[i]);
+        put_i(v); return SP_OK;
+    }
+    const bool isv = name.size() > 2 && name[0] == 'v' && name[1] == '_';
+    const bool ish = name.size() > 2 && name[0] == 'h' && name[1] == '_';
+    if (isv || ish) {
+        const size_t s = 2 * f + (isv ? 1 : 0);
+        const std::string sub = name.substr(2);
+        int n = 0; CK(d2h(&n, d.seg_n + s, 4));
+        if (sub == "idx") {
+            std::vector<float4> p(n); CK(d2h(p.data(), d.pts + s * N, (size_t)n * 16));
+            std::vector<int> v(n);
+            for (int i = 0; i < n; ++i) memcpy(&v[i], &p[i].w, 4);
+            put_i(v); return SP_OK;
+        }
+        if (sub == "root") {
+            std::vector<int> r(n), cs(n); CK(d2h(r.data(), d.root + s * N, (size_t)n * 4)); CK(d2h(cs.data(), d.csize + s * N, (size_t)n * 4));
+            for (int i = 0; i < n; ++i) { const int sz = cs[r[i]]; if (sz < ctx->d.c.min_c || sz > ctx->d.c.max_c) r[i] = -1; }
+            put_i(r); return SP_OK;
+        }
+        if (sub == "log") {
+            int ln = 0; CK(d2h(&ln, d.log_n + s, 4)); ln = std::min(ln, SP_LOGCAP);
+            std::vector<int> L((size_t)ln * 10); CK(d2h(L.data(), d.logs + s * SP_LOGCAP * 10, L.size() * 4));
+            std::vector<int> ord(ln); for (int i = 0; i < ln; ++i) ord[i] = i;
+            std::sort(ord.begin(), ord.end(), [&](int a, int b) { return L[a * 10] != L[b * 10] ? L[a * 10] < L[b * 10] : L[a * 10 + 1] < L[b * 10 + 1]; });
+            std::vector<int> o; for (int i : ord) o.insert(o.end(), L.begin() + i * 10, L.begin() + i * 10 + 10);
+            put_i(o); return SP_OK;
+        }
+        const bool seg = sub.rfind("seg_", 0) == 0, mrg = sub.rfind("merge_", 0) == 0;
+        if (seg || mrg) {
+            const std::string what = sub.substr(seg ? 4 : 6);
+            int nseg = 0, nm = 0; CK(d2h(&nseg, d.n_seg + s, 4)); CK(d2h(&nm, d.n_merged + s, 4));
+            std::vector<SpSegPlane> ch(SP_PSEG); std::vector<int> nx(SP_PSEG); std::vector<SpMergedPlane> mp(SP_PSEG);
+            CK(d2h(ch.data(), d.chunks + s * SP_PSEG, sizeof(SpSegPlane) * SP_PSEG)); CK(d2h(nx.data(), d.chunk_next + s * SP_PSEG, 4 * SP_PSEG));
+            CK(d2h(mp.data(), d.merged + s * SP_PSEG, sizeof(SpMergedPlane) * SP_PSEG));
+            std::vector<int> pp(n); CK(d2h(pp.data(), d.plane_pts + s * N, (size_t)n * 4));
+            std::vector<float> coef; std::vector<int> cnt, idx;
+            if (seg) {
+                for (int i = 0; i < nseg; ++i) { coef.insert(coef.end(), ch[i].coef, ch[i].coef + 4); cnt.push_back(ch[i].count); idx.insert(idx.end(), pp.begin() + ch[i].off, pp.begin() + ch[i].off + ch[i].count); }
+            } else {
+                for (int i = 0; i < nm; ++i) {
+                    coef.insert(coef.end(), mp[i].coef, mp[i].coef + 4); cnt.push_back(mp[i].count);
+                    for (int c = mp[i].head; c >= 0; c = nx[c]) idx.insert(idx.end(), pp.begin() + ch[c].off, pp.begin() + ch[c].off + ch[c].count);
+                }
+            }
+            if (what == "coef") { out.resize(coef.size() * 4); if (!coef.empty()) memcpy(out.data(), coef.data(), out.size()); return SP_OK; }
+            if (what == "count") { put_i(cnt); return SP_OK; }
+            if (what == "idx") { put_i(idx); return SP_OK; }
+        }
+    }
+    if (name == "plane_idx") {
+        sp_frame_result r; CK(d2h(&r, d.results + f, sizeof(r)));
+        std::vector<int> v(r.n_plane_points); CK(d2h(v.data(), d.plane_idx + f * N, (size_t)r.n_plane_points * 4));
+        put_i(v); return SP_OK;
+    }
+    ctx->err = "unknown tap: " + name;
+    return SP_ERR_ARG;
+}
+
+int64_t sp_tap_bytes(sp_ctx *ctx, int frame, const char *name)
+{
+    if (!ctx || !name) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::vector<uint8_t> v;
+    const int rc = tap_build(ctx, frame, name, v);
+    return rc < 0 ? rc : (int64_t)v.size();
+}
+
+int64_t sp_tap_copy(sp_ctx *ctx, int frame, const char *name, void *dst, int64_t cap)
+{
+    if (!ctx || !name || (!dst && cap > 0)) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::vector<uint8_t> v;
+    const int rc = tap_build(ctx, frame, name, v);
+    if (rc < 0) return rc;
+    const int64_t n = std::min<int64_t>(cap, (int64_t)v.size());
+    if (n > 0) memcpy(dst, v.data(), (size_t)n);
+    return n;
+}
+
+int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t *pixel_idx, int cap)
+{
+    if (!ctx || frame < 0 || frame >= ctx->last_nB || plane < 0 || cap < 0) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const SpDev &d = ctx->d;
+    const size_t N = ctx->N, f = frame;
+    sp_frame_result r; CK(cudaMemcpy(&r, d.results + f, sizeof(r), cudaMemcpyDeviceToHost));
+    if (plane >= r.n_planes) { ctx->err = "plane out of range"; return SP_ERR_ARG; }
+    const int n = std::min(cap, r.planes[plane].count);
+    std::vector<int> idx(n);
+    if (n) CK(cudaMemcpy(idx.data(), d.plane_idx + f * N + r.planes[plane].first, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (pixel_idx && n) memcpy(pixel_idx, idx.data(), (size_t)n * 4);
+    if (xyz && n) {
+        std::vector<float> a(N), b(N), c(N);
+        CK(cudaMemcpy(a.data(), d.x + f * N, N * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), d.y + f * N, N * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(c.data(), d.z + f * N, N * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) { xyz[3 * i] = a[idx[i]]; xyz[3 * i + 1] = b[idx[i]]; xyz[3 * i + 2] = c[idx[i]]; }
+    }
+    return n;
+}
+
+} /* extern "C" */

@@ -1,0 +1,153 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle: bit-exact for every integer output (voxel
+membership, representative picks, H/V labels, cluster labels, inlier masks, plane labels) and -- because the kernels
+evaluate the same un-fused float expressions in the same order -- for the float outputs too."""
+import numpy as np
+import pytest
+
+from parity import compare_frame, same_bits, BIT_EXACT_TAPS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx1(sp):
+    c = sp.Context(device=0, width=512, height=424, max_batch=1)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["0000", "0001"])
+def test_samples_bit_exact(sp, orc, samples, ctx1, name):
+    rec, w, h = samples[name]
+    res = ctx1.process_frames(rec)[0]
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(rec, w, h)
+    bad = compare_frame(ctx1, 0, res, o)
+    assert not bad, "\n".join(bad[:20])
+    assert int(res["n_planes"]) > 0
+
+
+@pytest.mark.parametrize("fid", [3, 11, 42])
+def test_synthetic_with_levelling(sp, orc, synth, ctx1, fid):
+    rec, R = synth.make_frame(fid)
+    res = ctx1.process_frames(rec, R.reshape(1, 9))[0]
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(rec, 512, 424, R)
+    bad = compare_frame(ctx1, 0, res, o)
+    assert not bad, "\n".join(bad[:20])
+    assert int(res["n_planes"]) >= 8
+
+
+def test_batch_equals_single_and_chunking(sp, orc, synth, samples):
+    recs = [samples["0000"][0], samples["0001"][0]]
+    Rs = [np.eye(3, dtype=np.float32).reshape(9)] * 2
+    for fid in (1, 2, 5):
+        r, R = synth.make_frame(fid)
+        recs.append(r)
+        Rs.append(R)
+    clouds = np.stack(recs)
+    R = np.stack(Rs)
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=3)      # 5 frames -> chunks of 3 + 2
+    res = ctx.process_frames(clouds, R)
+    assert len(res) == 5
+    for i in (3, 4):                                                     # last chunk holds frames 3, 4
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(recs[i], 512, 424, Rs[i])
+        bad = compare_frame(ctx, i - 3, res[i], o)
+        assert not bad, "frame %d\n" % i + "\n".join(bad[:20])
+    for i in (0, 1, 2):
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(recs[i], 512, 424, Rs[i])
+        oc = o.counts()
+        for k, v in oc.items():
+            assert int(res[i][k]) == v, (i, k)
+        op = o.tap("planes")
+        for j in range(len(op)):
+            for fld in op.dtype.names:
+                assert same_bits(res[i]["planes"][j][fld], op[j][fld]), (i, j, fld)
+    ctx.close()
+
+
+def test_device_resident_input(sp, orc, synth):
+    import torch
+    rec, R = synth.make_frame(9)
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=2)
+    dcloud = torch.from_numpy(np.stack([rec, rec]).view(np.uint8).reshape(2, -1)).cuda()
+    dR = torch.from_numpy(np.stack([R, R])).cuda()
+    torch.cuda.synchronize()
+    res = ctx.process_frames(dcloud, dR, device_input=True, nframes=2)
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(rec, 512, 424, R)
+    for f in (0, 1):
+        bad = compare_frame(ctx, f, res[f], o)
+        assert not bad, "\n".join(bad[:20])
+    ctx.close()
+
+
+def test_edge_cases(sp, orc, synth, ctx1):
+    rec, R = synth.make_frame(4)
+    # empty frame: every pixel invalid -> "<100 points" guard (StairPerception.cpp:56)
+    e = rec.copy()
+    e["rgba"] = 0
+    res = ctx1.process_frames(e, R.reshape(1, 9))[0]
+    assert int(res["status"]) == 1 and int(res["n_planes"]) == 0 and int(res["n_valid"]) == 0
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(e, 512, 424, R)
+    assert o.counts()["status"] == 1
+    # ragged: only 150 valid pixels in one corner patch
+    e = rec.copy()
+    keep = np.zeros((424, 512), dtype=bool)
+    keep[200:210, 100:115] = True
+    e["rgba"] = np.where(keep.reshape(-1), np.uint32(0xFF808080), np.uint32(0))
+    res = ctx1.process_frames(e, R.reshape(1, 9))[0]
+    o.process(e, 512, 424, R)
+    bad = compare_frame(ctx1, 0, res, o)
+    assert not bad, "\n".join(bad[:20])
+    # NaN coordinates in the input with valid colour
+    e = rec.copy()
+    e["x"][1000:5000] = np.nan
+    res = ctx1.process_frames(e, R.reshape(1, 9))[0]
+    o.process(e, 512, 424, R)
+    bad = compare_frame(ctx1, 0, res, o)
+    assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 6, 8, 9])
+def test_show_mode_taps(sp, orc, synth, ctx1, mode):
+    """process() returns early at every ShowModeDef tap (StairPerception.cpp:49-176)"""
+    rec, R = synth.make_frame(6)
+    res = ctx1.process_frames(rec, R.reshape(1, 9), show_mode=mode)[0]
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(rec, 512, 424, R, show_mode=mode)
+    assert int(res["n_planes"]) == 0
+    taps = {1: ["xyz", "normals"], 2: ["voxel_idx", "nonan_idx"], 3: ["noleg_idx"], 4: ["h_idx", "v_idx"],
+            6: ["h_seg_coef", "h_seg_idx"], 8: ["h_merge_coef", "h_merge_idx"], 9: ["v_merge_coef", "v_merge_idx"]}[mode]
+    for t in taps:
+        assert same_bits(ctx1.tap(0, t).reshape(-1), o.tap(t).reshape(-1)), t
+
+
+def test_other_parameters(sp, orc, synth):
+    """non-default knobs: tighter crop, coarser leaf, different thresholds"""
+    rec, R = synth.make_frame(8)
+    p = dict(sp.DEFAULT_PARAMS)
+    p.update(x_min=0.2, x_max=1.2, y_min=0.3, y_max=2.5, z_min=-0.6, z_max=0.6, voxel_x=0.02, voxel_y=0.015, voxel_z=0.02,
+             cluster_tolerance=0.05, seg_rest_point=120, seg_threshold=0.015, noleg_distance=0.5, parallel_angle_diff=15.0,
+             perpendicular_angle_diff=20.0, seg_max_iters=50)
+    ctx = sp.Context(p, device=0, width=512, height=424, max_batch=1)
+    res = ctx.process_frames(rec, R.reshape(1, 9))[0]
+    o = orc.Oracle(p)
+    o.process(rec, 512, 424, R)
+    bad = compare_frame(ctx, 0, res, o)
+    assert not bad, "\n".join(bad[:20])
+    ctx.close()
+
+
+def test_facade(sp, samples):
+    det = sp.StairDetection(sp.DEFAULT_PARAMS)
+    rec, w, h = samples["0001"]
+    has, planes, res = det.process(rec, "stair", width=w, height=h)
+    assert has and len(planes) == int(res["n_planes"])
+    for p in planes:
+        assert p["xyz"].shape == (int(p["record"]["count"]), 3)
+    has, planes, _ = det.process(rec, "original", width=w, height=h)
+    assert not has
