@@ -160,12 +160,14 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
     if (want_seg) {
-        CK(cudaMemsetAsync(d.head, 0xff, sizeof(int) * ((size_t)2 * nB << SP_HASH_BITS), st));
-        k_cl_build<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        CK(cudaMemsetAsync(d.ccnt, 0, sizeof(int) * ((size_t)2 * nB << SP_HASH_BITS), st));
+        k_cl_count<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_scan<<<2 * nB, 1024, 0, st>>>(d);
+        k_cl_scatter<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
         k_cl_union<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
         k_cl_flatten<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
         k_cl_rank<<<2 * nB, 256, 0, st>>>(d);
-        ctx->launches += 4;
+        ctx->launches += 6;
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     if (want_seg) {
@@ -257,8 +259,8 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
     DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
-    DA(d.pts, S * N); DA(d.seg_n, S); DA(d.head, S << SP_HASH_BITS);
-    DA(d.next, S * N); DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
+    DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
+    DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
     DA(d.n_clusters, S); DA(d.n_cand, S);
     DA(d.cand_root, S * SP_CMAX); DA(d.cand_size, S * SP_CMAX); DA(d.cand_off, S * SP_CMAX); DA(d.cand_slot, S * SP_CMAX);
     DA(d.wx, S * N); DA(d.wy, S * N); DA(d.wz, S * N); DA(d.wpix, S * N); DA(d.plane_pts, S * N);

@@ -91,8 +91,10 @@ struct SpDev {
     /* segments */
     float4 *pts;               /* [2B][N] {x, y, z, pixel} */
     int *seg_n;                /* [2B] */
-    int *head;                 /* [2B][1 << SP_HASH_BITS] */
-    int *next, *parent, *root, *csize;   /* [2B][N] */
+    int *ccnt;                 /* [2B][1 << SP_HASH_BITS] points per cell bucket (zero between chunks) */
+    int *cstart;               /* [2B][(1 << SP_HASH_BITS) + 1] exclusive scan of ccnt */
+    float4 *spts;              /* [2B][N] points in bucket-major order {x, y, z, list position} */
+    int *parent, *root, *csize;   /* [2B][N] */
     int *n_clusters;           /* [2B] clusters within [min,max] */
     int *n_cand;               /* [2B] */
     int *cand_root, *cand_size, *cand_off, *cand_slot;   /* [2B][SP_CMAX] */

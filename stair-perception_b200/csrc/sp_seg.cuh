@@ -18,19 +18,79 @@ __device__ __forceinline__ unsigned sp_cell_hash(int a, int b, int c)
     return ((unsigned)a * 73856093u) ^ ((unsigned)b * 19349663u) ^ ((unsigned)c * 83492791u);
 }
 
-__global__ void __launch_bounds__(256) k_cl_build(SpDev d)
+/* Cell grid of one segment: cell edge = cluster tolerance (x 1.0001), cells hashed into 1 << SP_HASH_BITS buckets.
+ * Three passes lay the points out bucket-major (a counting sort): count, scan, scatter.  Points of different
+ * cells that share a bucket are told apart by the distance test itself. */
+__device__ __forceinline__ unsigned sp_point_bucket(const float4 &p, float cell, int &a, int &b, int &c)
+{
+    a = (int)floorf(p.x / cell); b = (int)floorf(p.y / cell); c = (int)floorf(p.z / cell);
+    return sp_cell_hash(a, b, c) & ((1u << SP_HASH_BITS) - 1u);
+}
+
+__global__ void __launch_bounds__(256) k_cl_count(SpDev d)
 {
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = (size_t)s * d.N;
-    int *head = d.head + ((size_t)s << SP_HASH_BITS);
+    int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
     const float cell = d.c.cell;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = d.pts[base + i];
-        const int a = (int)floorf(p.x / cell), b = (int)floorf(p.y / cell), c = (int)floorf(p.z / cell);
-        const unsigned h = sp_cell_hash(a, b, c) & ((1u << SP_HASH_BITS) - 1u);
+        int a, b, c;
+        const unsigned h = sp_point_bucket(p, cell, a, b, c);
+        atomicAdd(&cnt[h], 1);
         d.parent[base + i] = i;
         d.csize[base + i] = 0;
-        d.next[base + i] = atomicExch(&head[h], i);
+    }
+}
+
+/* exclusive scan of one segment's bucket counts: one CTA of 1024 threads, 64 buckets per thread */
+__global__ void __launch_bounds__(1024) k_cl_scan(SpDev d)
+{
+    __shared__ int wsum[32];
+    const int s = blockIdx.x;
+    if (d.seg_n[s] == 0) return;
+    const int4 *cnt = reinterpret_cast<const int4 *>(d.ccnt + ((size_t)s << SP_HASH_BITS)) + threadIdx.x * 16;
+    int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
+    int4 v[16];
+    int tot = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { v[q] = cnt[q]; tot += v[q].x + v[q].y + v[q].z + v[q].w; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    int run = wsum[wid] + inc - tot;
+    int *o = start + threadIdx.x * 64;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        o[4 * q] = run; run += v[q].x; o[4 * q + 1] = run; run += v[q].y;
+        o[4 * q + 2] = run; run += v[q].z; o[4 * q + 3] = run; run += v[q].w;
+    }
+    if (threadIdx.x == 1023) start[1 << SP_HASH_BITS] = run;
+}
+
+__global__ void __launch_bounds__(256) k_cl_scatter(SpDev d)
+{
+    const int s = blockIdx.y, n = d.seg_n[s];
+    const size_t base = (size_t)s * d.N;
+    int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
+    const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
+    const float cell = d.c.cell;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = d.pts[base + i];
+        int a, b, c;
+        const unsigned h = sp_point_bucket(p, cell, a, b, c);
+        const int pos = start[h] + atomicSub(&cnt[h], 1) - 1;          /* drains the counters back to zero */
+        d.spts[base + pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
     }
 }
 
@@ -53,31 +113,34 @@ __device__ __forceinline__ void sp_uf_unite(int *parent, int a, int b)
     }
 }
 
+/* One thread per point in bucket-major order.  Every unordered pair of points in adjacent cells is tested exactly
+ * once: own cell against members with a smaller list position, plus the 13 "forward" neighbour cells.  (Two cells
+ * sharing a bucket only cause repeated, idempotent unions.)  Union-find is indexed by list position, so a
+ * component's root is its smallest member position whatever the visiting order. */
 __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
 {
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = (size_t)s * d.N;
-    const int *head = d.head + ((size_t)s << SP_HASH_BITS);
-    const int *next = d.next + base;
+    const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     int *parent = d.parent + base;
-    const float4 *pts = d.pts + base;
+    const float4 *sp = d.spts + base;
     const float cell = d.c.cell, r2 = d.c.r2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = pts[i];
-        const int a = (int)floorf(p.x / cell), b = (int)floorf(p.y / cell), c = (int)floorf(p.z / cell);
-        unsigned seen[27]; int ns = 0;
-        for (int da = -1; da <= 1; ++da) for (int db = -1; db <= 1; ++db) for (int dc = -1; dc <= 1; ++dc) {
-            const unsigned h = sp_cell_hash(a + da, b + db, c + dc) & ((1u << SP_HASH_BITS) - 1u);
-            bool dup = false;
-            for (int t = 0; t < ns; ++t) dup |= (seen[t] == h);
-            if (dup) continue;
-            seen[ns++] = h;
-            for (int j = head[h]; j >= 0; j = next[j]) {
-                if (j >= i) continue;
-                const float4 q = pts[j];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const float4 p = sp[t];
+        const int oi = __float_as_int(p.w);
+        int a, b, c;
+        const unsigned h0 = sp_point_bucket(p, cell, a, b, c);
+        for (int k = 13; k < 27; ++k) {                                  /* offsets (0,0,0) then the 13 forward ones */
+            const int da = k / 9 - 1, db = (k / 3) % 3 - 1, dc = k % 3 - 1;
+            const unsigned h = k == 13 ? h0 : (sp_cell_hash(a + da, b + db, c + dc) & ((1u << SP_HASH_BITS) - 1u));
+            const int j1 = start[h + 1];
+            for (int j = start[h]; j < j1; ++j) {
+                const float4 q = sp[j];
+                const int oj = __float_as_int(q.w);
+                if (k == 13 && oj >= oi) continue;
                 const float d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
-                float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;
-                if (dist < r2) sp_uf_unite(parent, i, j);
+                float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
+                if (dist < r2 && parent[oi] != parent[oj]) sp_uf_unite(parent, oi, oj);
             }
         }
     }
