@@ -147,6 +147,13 @@ const char *sp_stage_name(int i);
 /* number of kernels this library launched since sp_create (its own + CUB) */
 int64_t sp_launch_count(const sp_ctx *ctx);
 
+/* Per-kernel trace of the last chunk (the reference's TIME_RECORD per-stage timers, StairPerception.hpp:13,181-190,
+ * at kernel granularity).  Off by default; sp_set_trace(ctx, 1) or the environment variable SP_TRACE=1 makes the
+ * library record a CUDA event after every launch.  sp_trace_ms(ctx, -1, 0, 0) returns the number of entries;
+ * sp_trace_ms(ctx, i, &name, &ms) the i-th entry's kernel name and duration. */
+void sp_set_trace(sp_ctx *ctx, int on);
+int sp_trace_ms(sp_ctx *ctx, int i, const char **name, float *ms);
+
 /* Run only one stage on device-resident inputs (bench / profiling of a single kernel family).
  * stage: 0 = ingest+normals, 1 = voxel (key+sort+pick), 2 = whole pipeline w/o D2H. */
 int sp_run_stage_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int stage);

@@ -67,6 +67,8 @@ def lib():
         L.sp_launch_count.restype = C.c_int64
         L.sp_launch_count.argtypes = [C.c_void_p]
         L.sp_run_stage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sp_set_trace.argtypes = [C.c_void_p, C.c_int]
+        L.sp_trace_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
         L.sp_stream.restype = C.c_void_p
         L.sp_stream.argtypes = [C.c_void_p]
         _lib = L
@@ -189,6 +191,18 @@ class Context:
         arr = (C.c_float * 16)()
         n = self.L.sp_stage_ms(self.h, arr, 16)
         return {self.L.sp_stage_name(i).decode(): float(arr[i]) for i in range(n)}
+
+    def set_trace(self, on=True):
+        self.L.sp_set_trace(self.h, 1 if on else 0)
+
+    def trace_ms(self):
+        """[(kernel name, ms)] of the last chunk, in launch order (needs set_trace / SP_TRACE=1)"""
+        out = []
+        for i in range(max(0, self.L.sp_trace_ms(self.h, -1, None, None))):
+            nm, ms = C.c_char_p(), C.c_float()
+            if self.L.sp_trace_ms(self.h, i, C.byref(nm), C.byref(ms)) == 0:
+                out.append((nm.value.decode(), float(ms.value)))
+        return out
 
     def launch_count(self):
         return int(self.L.sp_launch_count(self.h))

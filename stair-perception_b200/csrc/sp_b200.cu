@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <random>
@@ -109,6 +110,11 @@ struct sp_ctx {
     cudaEvent_t ev[STG_COUNT + 1];
     cudaEvent_t ev_in[2], ev_done[2];
     float stage_ms[STG_COUNT];
+    /* per-kernel trace of the last chunk (SP_TRACE=1 or sp_set_trace): one event after every launch */
+    bool trace = false;
+    std::vector<cudaEvent_t> tev;
+    std::vector<const char *> tname;
+    int tn = 0;
     int last_nB = 0;
     int64_t launches = 0;
     std::string err;
@@ -129,7 +135,20 @@ template <class T> cudaError_t dalloc(sp_ctx *ctx, T **p, size_t n)
 
 int frame_bits(int B) { int b = 0; while ((1 << b) < B) ++b; return b; }
 
-/* the per-chunk launch sequence; `upto` = last stage group to run */
+/* trace mark: an event after the launch(es) named `name` (no-op unless tracing) */
+void mark(sp_ctx *ctx, const char *name)
+{
+    if (!ctx->trace) return;
+    if (ctx->tn >= (int)ctx->tev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->tev.push_back(e); ctx->tname.push_back(name);
+    }
+    ctx->tname[ctx->tn] = name;
+    cudaEventRecord(ctx->tev[ctx->tn++], ctx->stream);
+}
+
+/* the per-chunk launch sequence; only_stage: -1 = everything `show_mode` asks for, 0 / 1 = one stage group, 2 = all */
 int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int show_mode, int only_stage)
 {
     SpDev d = ctx->d;
@@ -137,56 +156,79 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     cudaStream_t st = ctx->stream;
     const int N = ctx->N;
     ctx->last_nB = nB;
+    ctx->tn = 0;
     const bool all = only_stage < 0 || only_stage == 2;
+    mark(ctx, "begin");
     CK(cudaEventRecord(ctx->ev[0], st));
     if (all || only_stage == 0) {
         k_init_frames<<<(nB * SP_NCOUNT + 255) / 256, 256, 0, st>>>(d, nB);
+        mark(ctx, "k_init_frames");
         dim3 g((ctx->W + K1_TW - 1) / K1_TW, (ctx->H + K1_TH - 1) / K1_TH, nB);
         k_ingest_normals<<<g, K1_THREADS, sizeof(K1Smem), st>>>(d);
+        mark(ctx, "k_ingest_normals");
         ctx->launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
     if (want_voxel) {
         k_frame_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, nB);
+        mark(ctx, "k_frame_grid");
         k_voxel_key<<<dim3(std::min(d.nblk, 148), nB), 256, 0, st>>>(d);
+        mark(ctx, "k_voxel_key");
         size_t tb = ctx->cub_bytes;
         CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)nB * N, 0, 32 + frame_bits(nB), st));
+        mark(ctx, "radix_sort");
         k_voxel_pick<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        mark(ctx, "k_voxel_pick");
         k_scan_blocks<<<nB, 256, 0, st>>>(d);
+        mark(ctx, "k_scan_blocks");
         k_scatter_lists<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        mark(ctx, "k_scatter_lists");
         ctx->launches += 5 + 2 + (32 + frame_bits(nB) + 7) / 8;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
     if (want_seg) {
         CK(cudaMemsetAsync(d.ccnt, 0, sizeof(int) * ((size_t)2 * nB << SP_HASH_BITS), st));
+        mark(ctx, "memset_ccnt");
         k_cl_count<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        mark(ctx, "k_cl_count");
         k_cl_scan<<<2 * nB, 1024, 0, st>>>(d);
+        mark(ctx, "k_cl_scan");
         k_cl_scatter<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        mark(ctx, "k_cl_scatter");
         k_cl_union<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        mark(ctx, "k_cl_union");
         k_cl_flatten<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        mark(ctx, "k_cl_flatten");
         k_cl_rank<<<2 * nB, 256, 0, st>>>(d);
+        mark(ctx, "k_cl_rank");
         ctx->launches += 6;
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     if (want_seg) {
         k_clear_planes<<<(2 * nB * SP_PSEG + 255) / 256, 256, 0, st>>>(d, 2 * nB);
+        mark(ctx, "k_clear_planes");
         k_ransac<<<dim3(SP_CMAX, 2 * nB), 256, 0, st>>>(d);
+        mark(ctx, "k_ransac");
         ctx->launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[4], st));
     if (all) {
         if (want_seg) {
             k_merge<<<(nB + 31) / 32, 32, 0, st>>>(d, nB);
+            mark(ctx, "k_merge");
             ctx->launches += 1;
             if (show_mode >= SP_SHOW_STAIR) {
                 k_plane_stats<<<dim3(SP_PSEG, 2 * nB), 256, 0, st>>>(d);
+                mark(ctx, "k_plane_stats");
                 ctx->launches += 1;
             }
         }
         k_finalize<<<(nB + 63) / 64, 64, 0, st>>>(d, nB, ctx->d_order, (want_seg && show_mode >= SP_SHOW_STAIR) ? 1 : 0);
+        mark(ctx, "k_finalize");
         k_gather_plane_points<<<dim3(SP_MAX_PLANES, nB), 256, 0, st>>>(d, ctx->d_order);
+        mark(ctx, "k_gather_plane_points");
         ctx->launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[5], st));
@@ -233,6 +275,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     }
     sp_ctx *ctx = new sp_ctx();
     ctx->device = device; ctx->W = width; ctx->H = height; ctx->N = width * height; ctx->B = max_batch;
+    { const char *t = getenv("SP_TRACE"); ctx->trace = t && *t && *t != '0'; }
     memset(&ctx->d, 0, sizeof(ctx->d));
     memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
     auto fail = [&](const char *what, cudaError_t err) {
@@ -305,6 +348,7 @@ void sp_destroy(sp_ctx *ctx)
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     for (int i = 0; i <= STG_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
+    for (cudaEvent_t e : ctx->tev) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -412,6 +456,21 @@ int sp_stage_ms(sp_ctx *ctx, float *out, int cap)
     return n;
 }
 const char *sp_stage_name(int i) { return (i >= 0 && i < STG_COUNT) ? kStageNames[i] : ""; }
+
+void sp_set_trace(sp_ctx *ctx, int on) { if (ctx) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->trace = on != 0; ctx->tn = 0; } }
+
+int sp_trace_ms(sp_ctx *ctx, int i, const char **name, float *ms)
+{
+    if (!ctx) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (i < 0) return std::max(0, ctx->tn - 1);
+    if (i + 1 >= ctx->tn || !name || !ms) return SP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    *name = ctx->tname[i + 1];
+    if (cudaEventElapsedTime(ms, ctx->tev[i], ctx->tev[i + 1]) != cudaSuccess) { *ms = 0.f; (void)cudaGetLastError(); }
+    return SP_OK;
+}
 int64_t sp_launch_count(const sp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 /* ------------------------------------------------------------------------------------------------ taps */

@@ -24,6 +24,7 @@ clouds = torch.from_numpy(np.tile(recs.view(np.uint8).reshape(nd, Nb), ((frames 
 R = torch.from_numpy(np.tile(Rs, ((frames + nd - 1) // nd, 1))[:frames].copy()).cuda()
 torch.cuda.synchronize()
 ctx = sp.Context(device=0, width=512, height=424, max_batch=frames)
+ctx.set_trace(True)
 for _ in range(passes):
     if stage < 0:
         res = ctx.process_frames(clouds, R, device_input=True, nframes=frames)
@@ -31,6 +32,11 @@ for _ in range(passes):
         ctx.run_stage_device(clouds.data_ptr(), R.data_ptr(), frames, stage)
         ctx.stage_ms()
 print("stage ms:", ctx.stage_ms())
+tr = ctx.trace_ms()
+tot = sum(ms for _, ms in tr)
+for nm, ms in tr:
+    print("  %-24s %9.3f ms  %5.1f%%" % (nm, ms, 100 * ms / max(tot, 1e-9)))
+print("  %-24s %9.3f ms" % ("total", tot))
 if stage < 0:
     print("planes:", res["n_planes"][:8].tolist(), "status:", res["status"][:8].tolist())
 ctx.close()
