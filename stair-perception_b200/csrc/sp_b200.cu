@@ -201,7 +201,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_cl_union");
         k_cl_flatten<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_flatten");
-        k_cl_rank<<<2 * nB, 256, 0, st>>>(d);
+        k_cl_rank<<<2 * nB, RK_THREADS, 0, st>>>(d);
         mark(ctx, "k_cl_rank");
         ctx->launches += 6;
     }
@@ -209,7 +209,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     if (want_seg) {
         k_clear_planes<<<(2 * nB * SP_PSEG + 255) / 256, 256, 0, st>>>(d, 2 * nB);
         mark(ctx, "k_clear_planes");
-        k_ransac<<<dim3(SP_CMAX, 2 * nB), 256, 0, st>>>(d);
+        k_ransac<<<dim3(SP_CMAX, 2 * nB), RS_THREADS, 0, st>>>(d);
         mark(ctx, "k_ransac");
         ctx->launches += 2;
     }
@@ -220,7 +220,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
             mark(ctx, "k_merge");
             ctx->launches += 1;
             if (show_mode >= SP_SHOW_STAIR) {
-                k_plane_stats<<<dim3(SP_PSEG, 2 * nB), 256, 0, st>>>(d);
+                k_plane_stats<<<dim3(SP_PSEG, 2 * nB), PS_THREADS, 0, st>>>(d);
                 mark(ctx, "k_plane_stats");
                 ctx->launches += 1;
             }
@@ -307,6 +307,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     DA(d.n_clusters, S); DA(d.n_cand, S);
     DA(d.cand_root, S * SP_CMAX); DA(d.cand_size, S * SP_CMAX); DA(d.cand_off, S * SP_CMAX); DA(d.cand_slot, S * SP_CMAX);
     DA(d.wx, S * N); DA(d.wy, S * N); DA(d.wz, S * N); DA(d.wpix, S * N); DA(d.plane_pts, S * N);
+    DA(d.vx, S * N); DA(d.vy, S * N); DA(d.vz, S * N); DA(d.vpix, S * N); DA(d.plane_x, S * N); DA(d.plane_y, S * N); DA(d.plane_z, S * N);
     DA(d.seg_planes, S * SP_PSEG); DA(d.logs, S * SP_LOGCAP * 10); DA(d.log_n, S);
     DA(d.n_seg, S); DA(d.chunks, S * SP_PSEG); DA(d.chunk_next, S * SP_PSEG); DA(d.merged, S * SP_PSEG); DA(d.n_merged, S);
     DA(d.info, S * SP_PSEG); DA(d.results, B); DA(d.plane_idx, BN); DA(ctx->d_order, B * SP_MAX_PLANES);

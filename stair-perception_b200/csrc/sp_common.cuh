@@ -98,8 +98,10 @@ struct SpDev {
     int *n_clusters;           /* [2B] clusters within [min,max] */
     int *n_cand;               /* [2B] */
     int *cand_root, *cand_size, *cand_off, *cand_slot;   /* [2B][SP_CMAX] */
-    float *wx, *wy, *wz; int *wpix;      /* [2B][N] cluster workspaces */
+    float *wx, *wy, *wz; int *wpix;      /* [2B][N] cluster workspaces: points cluster by cluster (k_cl_rank) */
+    float *vx, *vy, *vz; int *vpix;      /* [2B][N] twin workspaces (k_ransac ping-pongs the shrinking remainder) */
     int *plane_pts;            /* [2B][N] pixel lists of the planes */
+    float *plane_x, *plane_y, *plane_z;  /* [2B][N] their coordinates, same order */
     SpSegPlane *seg_planes;    /* [2B][SP_PSEG] */
     int *logs, *log_n;         /* [2B][SP_LOGCAP][10], [2B] */
     /* merge + stats */

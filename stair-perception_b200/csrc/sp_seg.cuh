@@ -160,17 +160,25 @@ __global__ void __launch_bounds__(256) k_cl_flatten(SpDev d)
 }
 
 /* One CTA per segment: count clusters within [min,max]; collect those that can yield a plane (size >= rest),
- * rank them like PCL (size descending; ties: smaller first member), lay out their workspaces and plane slots. */
-__global__ void __launch_bounds__(256) k_cl_rank(SpDev d)
+ * rank them like PCL (size descending; ties: smaller first member), lay out their workspaces and plane slots; then
+ * lay the candidate clusters' points out contiguously, cluster by cluster in rank order, members in ascending
+ * position order (what pointCluster's per-cluster clouds hold, StairPerception.cpp:951-962) -- a stable multi-way
+ * partition: per-warp contiguous chunks, per-(warp, cluster) counts via __match_any_sync, one prefix pass. */
+#define RK_THREADS 1024
+#define RK_WARPS (RK_THREADS / 32)
+__global__ void __launch_bounds__(RK_THREADS) k_cl_rank(SpDev d)
 {
     __shared__ int c_root[1024], c_size[1024];
+    __shared__ int cnt[RK_WARPS][SP_CMAX + 1];
     __shared__ int nc, nvalid;
     const int s = blockIdx.x, n = d.seg_n[s];
     const size_t base = (size_t)s * d.N;
+    int *crank = d.parent + base;                       /* union-find storage is free again: cluster rank per root position */
     if (threadIdx.x == 0) { nc = 0; nvalid = 0; }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (d.root[base + i] != i) continue;
+        crank[i] = -1;
         const int sz = d.csize[base + i];
         if (sz < d.c.min_c || sz > d.c.max_c) continue;
         atomicAdd(&nvalid, 1);
@@ -192,7 +200,41 @@ __global__ void __launch_bounds__(256) k_cl_rank(SpDev d)
         if (rank < SP_CMAX) {
             d.cand_root[s * SP_CMAX + rank] = c_root[a]; d.cand_size[s * SP_CMAX + rank] = c_size[a];
             d.cand_off[s * SP_CMAX + rank] = off; d.cand_slot[s * SP_CMAX + rank] = slot;
+            crank[c_root[a]] = rank;
         }
+    }
+    for (int i = threadIdx.x; i < RK_WARPS * (SP_CMAX + 1); i += blockDim.x) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int CC = min(C, SP_CMAX);
+    if (CC == 0) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int L = ((n + RK_THREADS - 1) / RK_THREADS) * 32;              /* chunk per warp, a multiple of 32 */
+    const unsigned lt = (1u << lane) - 1u;
+    for (int g = 0; g < L; g += 32) {
+        const int i = w * L + g + lane;
+        const int key = i < n ? crank[d.root[base + i]] : -1;
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && (m & lt) == 0) cnt[w][key] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < CC) {
+        int run = d.cand_off[s * SP_CMAX + threadIdx.x];
+        for (int q = 0; q < RK_WARPS; ++q) { const int t = cnt[q][threadIdx.x]; cnt[q][threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+    for (int g = 0; g < L; g += 32) {
+        const int i = w * L + g + lane;
+        const int key = i < n ? crank[d.root[base + i]] : -1;
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (key >= 0) {
+            const int pos = cnt[w][key] + __popc(m & lt);
+            const float4 q = d.pts[base + i];
+            d.wx[base + pos] = q.x; d.wy[base + pos] = q.y; d.wz[base + pos] = q.z; d.wpix[base + pos] = __float_as_int(q.w);
+        }
+        __syncwarp();
+        if (key >= 0 && (m & lt) == 0) cnt[w][key] += __popc(m);
+        __syncwarp();
     }
 }
 
@@ -200,21 +242,32 @@ __global__ void __launch_bounds__(256) k_cl_rank(SpDev d)
 /* RANSAC plane extraction: one CTA per (segment, cluster).  Restates pcl::SACSegmentation::segment with
  * RandomSampleConsensus (ransac.hpp), the index-shuffle sampler of SampleConsensusModel (sac_model.h) driven by
  * boost::mt19937(12345), SampleConsensusModelPlane / ParallelPlane and the callers' extract-until-small loops
- * (StairPerception.cpp:773-808, :853-884).  Hypotheses are drawn by one thread, scored SP_ROUND at a time by
- * the whole CTA (register counters -> __reduce_add_sync -> shared atomics), then the sequential
- * "first strictly better wins / adaptive k" rule is replayed exactly. */
+ * (StairPerception.cpp:773-808, :853-884).
+ *   - the cluster's points arrive contiguous (k_cl_rank) in wx/wy/wz/wpix; every extraction writes the remainder
+ *     to the twin buffers (ping-pong), so no pass is ordered by a barrier chain;
+ *   - hypotheses are drawn by one thread, scored SP_ROUND at a time by the whole CTA (register counters ->
+ *     __reduce_add_sync -> shared atomics), then the sequential "first strictly better wins / adaptive k" rule is
+ *     replayed exactly;
+ *   - the refit's nine single-pass float sums (computeMeanAndCovarianceMatrix) must be added in index order: warp 0
+ *     is the "summer" (lane q owns accumulator q, one FADD per element on the critical path), the other warps stage
+ *     the nine products per point, double-buffered, with +0.0f for non-inliers (adding +0 never changes a float sum
+ *     that started at +0). */
+#define RS_THREADS 256
+#define RS_TILE (RS_THREADS - 32)
+#define RS_NW (RS_THREADS / 32)
 struct RsSmem {
     int map_key[1024], map_val[1024];
     float4 model[SP_ROUND];
     int tri[SP_ROUND][3];
     int mvalid[SP_ROUND];
     int counts[SP_ROUND];
-    int wsum[33];
     int n_round, done, have, mt_pos, map_n, overflow;
     float best_m[4], refined[4];
     int best_tri[3], best_count, scored;
     float accu[9];
-    int n_inl;
+    int n_inl, slot;
+    int wcnt[RS_NW], wbase[RS_NW];
+    float4 stage[2][RS_TILE][3];
 };
 
 __device__ __forceinline__ int rs_map_get(RsSmem &S, int k)
@@ -249,35 +302,23 @@ __device__ __forceinline__ bool rs_model_valid(const SpConst &c, bool parallel, 
     return !((double)fabsf(c0) > c.sin_angle);
 }
 
-__global__ void __launch_bounds__(256) k_ransac(SpDev d)
+__global__ void __launch_bounds__(RS_THREADS) k_ransac(SpDev d)
 {
     __shared__ RsSmem S;
     const int s = blockIdx.y, ci = blockIdx.x;
     if (ci >= d.n_cand[s]) return;
     const bool vertical = (s & 1) != 0;
     const size_t base = (size_t)s * d.N;
-    const int tid = threadIdx.x;
-    const int my_root = d.cand_root[s * SP_CMAX + ci];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int off = d.cand_off[s * SP_CMAX + ci];
-    const int size0 = d.cand_size[s * SP_CMAX + ci];
+    /* current / other point buffers of this cluster (ping-pong across extractions) */
     float *X = d.wx + base + off, *Y = d.wy + base + off, *Z = d.wz + base + off;
     int *PIX = d.wpix + base + off;
+    float *X2 = d.vx + base + off, *Y2 = d.vy + base + off, *Z2 = d.vz + base + off;
+    int *PIX2 = d.vpix + base + off;
     int *OUT = d.plane_pts + base + off;
-    const int nseg = d.seg_n[s];
-
-    /* gather the cluster's members in ascending position order */
-    {
-        int w = 0;
-        for (int i0 = 0; i0 < nseg; i0 += blockDim.x) {
-            const int i = i0 + tid;
-            const bool mine = i < nseg && d.root[base + i] == my_root;
-            int tot; const int p = sp_block_scan_flag(mine, S.wsum, &tot);
-            if (mine) { const float4 q = d.pts[base + i]; X[w + p] = q.x; Y[w + p] = q.y; Z[w + p] = q.z; PIX[w + p] = __float_as_int(q.w); }
-            w += tot;
-        }
-    }
-    __syncthreads();
-    int n = size0, out_n = 0, call = 0;
+    float *OX = d.plane_x + base + off, *OY = d.plane_y + base + off, *OZ = d.plane_z + base + off;
+    int n = d.cand_size[s * SP_CMAX + ci], out_n = 0, call = 0;
     const int rest = d.c.rest;
     const float thr = d.c.seg_thr;
 
@@ -294,9 +335,12 @@ __global__ void __launch_bounds__(256) k_ransac(SpDev d)
         const unsigned max_skip = (unsigned)d.c.max_iters * 10u;
         while (!S.done) {
             if (tid == 0) {
-                /* draw up to SP_ROUND samples (SampleConsensusModel::getSamples / drawIndexSample) */
+                /* draw up to SP_ROUND samples (SampleConsensusModel::getSamples / drawIndexSample); no more than the
+                 * adaptive rule can still consume */
+                int want = SP_ROUND;
+                { const double left = k - (double)iterations; if (left < (double)SP_ROUND) want = max(1, (int)ceil(left)); }
                 int nr = 0;
-                for (; nr < SP_ROUND; ++nr) {
+                for (; nr < want; ++nr) {
                     bool good = false; int t0 = 0, t1 = 0, t2 = 0;
                     for (int it = 0; it < 1000 && !good; ++it) {
                         if (S.mt_pos + 3 > SP_MT_LEN || S.overflow) { S.overflow = 1; break; }
@@ -331,19 +375,31 @@ __global__ void __launch_bounds__(256) k_ransac(SpDev d)
                 int cnt[SP_ROUND];
 #pragma unroll
                 for (int h = 0; h < SP_ROUND; ++h) cnt[h] = 0;
-                for (int i = tid; i < n; i += blockDim.x) {
-                    const float px = X[i], py = Y[i], pz = Z[i];
+                if (nr > 2) {
+                    for (int i = tid; i < n; i += blockDim.x) {
+                        const float px = X[i], py = Y[i], pz = Z[i];
 #pragma unroll
-                    for (int h = 0; h < SP_ROUND; ++h) {
-                        const float4 m = S.model[h];
-                        const float dd = fabsf(sp_dot4(m.x, m.y, m.z, m.w, px, py, pz, 1.0f));
-                        cnt[h] += (h < nr && dd < thr) ? 1 : 0;
+                        for (int h = 0; h < SP_ROUND; ++h) {
+                            const float4 m = S.model[h];
+                            const float dd = fabsf(sp_dot4(m.x, m.y, m.z, m.w, px, py, pz, 1.0f));
+                            cnt[h] += (h < nr && dd < thr) ? 1 : 0;
+                        }
+                    }
+                } else {
+                    for (int i = tid; i < n; i += blockDim.x) {
+                        const float px = X[i], py = Y[i], pz = Z[i];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float4 m = S.model[h];
+                            const float dd = fabsf(sp_dot4(m.x, m.y, m.z, m.w, px, py, pz, 1.0f));
+                            cnt[h] += (h < nr && dd < thr) ? 1 : 0;
+                        }
                     }
                 }
 #pragma unroll
                 for (int h = 0; h < SP_ROUND; ++h) {
                     const int c = __reduce_add_sync(0xffffffffu, cnt[h]);
-                    if ((tid & 31) == 0 && c) atomicAdd(&S.counts[h], c);
+                    if (lane == 0 && c) atomicAdd(&S.counts[h], c);
                 }
             }
             __syncthreads();
@@ -377,25 +433,39 @@ __global__ void __launch_bounds__(256) k_ransac(SpDev d)
         int n_inl = 0;
         if (S.have) {
             /* optimizeModelCoefficients: single-pass float mean + covariance over the inliers of the best model, in
-             * index order (computeMeanAndCovarianceMatrix); thread q owns accumulator q */
+             * index order (computeMeanAndCovarianceMatrix) */
             const float m0 = S.best_m[0], m1 = S.best_m[1], m2 = S.best_m[2], m3 = S.best_m[3];
             const bool bvalid = rs_model_valid(d.c, vertical, S.best_m);
-            if (tid < 9 && bvalid) {
-                float acc = 0.f; int cnt = 0;
-                for (int i = 0; i < n; ++i) {
-                    const float px = X[i], py = Y[i], pz = Z[i];
-                    if (fabsf(sp_dot4(m0, m1, m2, m3, px, py, pz, 1.0f)) < thr) {
-                        float t;
-                        switch (tid) {
-                            case 0: t = px * px; break; case 1: t = px * py; break; case 2: t = px * pz; break;
-                            case 3: t = py * py; break; case 4: t = py * pz; break; case 5: t = pz * pz; break;
-                            case 6: t = px; break; case 7: t = py; break; default: t = pz; break;
+            if (bvalid) {
+                const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+                float acc = 0.f; int mycnt = 0;
+                for (int t = 0; t <= ntiles; ++t) {
+                    if (wid > 0) {
+                        const int e = t * RS_TILE + (tid - 32);
+                        if (t < ntiles && e < n) {
+                            const float px = X[e], py = Y[e], pz = Z[e];
+                            const bool inl = fabsf(sp_dot4(m0, m1, m2, m3, px, py, pz, 1.0f)) < thr;
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+                            if (inl) { a = make_float4(px * px, px * py, px * pz, py * py); b = make_float4(py * pz, pz * pz, px, py); c.x = pz; ++mycnt; }
+                            float4 *dst = S.stage[t & 1][tid - 32];
+                            dst[0] = a; dst[1] = b; dst[2] = c;
                         }
-                        acc += t; ++cnt;
+                    } else if (t > 0 && lane < 9) {
+                        const int cnt = min(RS_TILE, n - (t - 1) * RS_TILE);
+                        const float *src = reinterpret_cast<const float *>(S.stage[(t - 1) & 1]) + lane;
+                        int e = 0;
+                        for (; e + 8 <= cnt; e += 8) {
+                            const float v0 = src[(e + 0) * 12], v1 = src[(e + 1) * 12], v2 = src[(e + 2) * 12], v3 = src[(e + 3) * 12];
+                            const float v4 = src[(e + 4) * 12], v5 = src[(e + 5) * 12], v6 = src[(e + 6) * 12], v7 = src[(e + 7) * 12];
+                            acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+                        }
+                        for (; e < cnt; ++e) acc += src[e * 12];
                     }
+                    __syncthreads();
                 }
-                S.accu[tid] = acc;
-                if (tid == 0) S.n_inl = cnt;
+                if (wid == 0 && lane < 9) S.accu[lane] = acc;
+                mycnt = __reduce_add_sync(0xffffffffu, mycnt);
+                if (lane == 0 && mycnt) atomicAdd(&S.n_inl, mycnt);
             }
             __syncthreads();
             if (tid == 0) {
@@ -418,62 +488,68 @@ __global__ void __launch_bounds__(256) k_ransac(SpDev d)
                 S.mvalid[0] = rs_model_valid(d.c, vertical, refined) ? 1 : 0;
             }
             __syncthreads();
-            /* selectWithinDistance on the refined model, then split the cluster preserving order */
-            const float f0 = S.refined[0], f1 = S.refined[1], f2 = S.refined[2], f3 = S.refined[3];
-            const bool rvalid = S.mvalid[0] != 0;
-            int cnt = 0;
-            for (int i = tid; i < n; i += blockDim.x)
-                cnt += (rvalid && fabsf(sp_dot4(f0, f1, f2, f3, X[i], Y[i], Z[i], 1.0f)) < thr) ? 1 : 0;
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (tid == 0) S.counts[0] = 0;
-            __syncthreads();
-            if ((tid & 31) == 0 && cnt) atomicAdd(&S.counts[0], cnt);
-            __syncthreads();
-            n_inl = S.counts[0];
         }
-        /* plane slots come from a per-segment pool; k_merge orders them by (cluster rank, call) */
+        /* selectWithinDistance on the refined model: every warp owns a contiguous chunk; count first */
+        const float f0 = S.refined[0], f1 = S.refined[1], f2 = S.refined[2], f3 = S.refined[3];
+        const bool rvalid = S.have && S.mvalid[0] != 0;
+        const int L = ((n + RS_THREADS - 1) / RS_THREADS) * 32;
+        {
+            int cnt = 0;
+            if (rvalid)
+                for (int g = 0; g < L; g += 32) {
+                    const int i = wid * L + g + lane;
+                    cnt += (i < n && fabsf(sp_dot4(f0, f1, f2, f3, X[i], Y[i], Z[i], 1.0f)) < thr) ? 1 : 0;
+                }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) S.wcnt[wid] = cnt;
+        }
+        __syncthreads();
         if (tid == 0) {
+            int run = 0;
+            for (int q = 0; q < RS_NW; ++q) { S.wbase[q] = run; run += S.wcnt[q]; }
+            n_inl = run;
+            /* plane slots come from a per-segment pool; k_merge orders them by (cluster rank, call) */
             int slot = -1;
             if (S.have && n_inl >= rest) {
                 slot = atomicAdd(&d.n_seg[s], 1);
                 if (slot >= SP_PSEG) { slot = -1; atomicOr(&d.flags[s >> 1], 4); }
             }
-            S.n_round = slot;
-        }
-        __syncthreads();
-        const int slot = S.n_round;
-        const bool emit = slot >= 0;
-        if (tid == 0) {
+            S.slot = slot; S.n_inl = n_inl;
             const int row = atomicAdd(&d.log_n[s], 1);
             if (row < SP_LOGCAP) {
-                int *L = d.logs + ((size_t)s * SP_LOGCAP + row) * 10;
-                L[0] = ci; L[1] = call; L[2] = n; L[3] = S.scored; L[4] = S.best_tri[0]; L[5] = S.best_tri[1]; L[6] = S.best_tri[2];
-                L[7] = S.best_count; L[8] = S.have ? n_inl : 0; L[9] = emit ? 1 : 0;
+                int *Lg = d.logs + ((size_t)s * SP_LOGCAP + row) * 10;
+                Lg[0] = ci; Lg[1] = call; Lg[2] = n; Lg[3] = S.scored; Lg[4] = S.best_tri[0]; Lg[5] = S.best_tri[1]; Lg[6] = S.best_tri[2];
+                Lg[7] = S.best_count; Lg[8] = S.have ? n_inl : 0; Lg[9] = slot >= 0 ? 1 : 0;
             }
         }
+        __syncthreads();
+        const int slot = S.slot;
+        n_inl = S.n_inl;
         ++call;
-        if (!emit) break;
+        if (slot < 0) break;
         {
-            const float f0 = S.refined[0], f1 = S.refined[1], f2 = S.refined[2], f3 = S.refined[3];
-            int w_in = 0, w_out = 0;
-            for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-                const int i = i0 + tid;
-                float px = 0.f, py = 0.f, pz = 0.f; int pix = 0; bool inl = false, act = i < n;
+            /* split the cluster preserving order: inliers -> the plane's point list, the rest -> the twin buffers */
+            const unsigned lt = (1u << lane) - 1u;
+            int w_in = S.wbase[wid], w_out = wid * L - S.wbase[wid];
+            const bool keep_rest = (n - n_inl) >= rest;
+            for (int g = 0; g < L; g += 32) {
+                const int i = wid * L + g + lane;
+                float px = 0.f, py = 0.f, pz = 0.f; int pix = 0; bool inl = false;
+                const bool act = i < n;
                 if (act) { px = X[i]; py = Y[i]; pz = Z[i]; pix = PIX[i]; inl = fabsf(sp_dot4(f0, f1, f2, f3, px, py, pz, 1.0f)) < thr; }
-                int tin; const int pin = sp_block_scan_flag(act && inl, S.wsum, &tin);
-                int tout; const int pout = sp_block_scan_flag(act && !inl, S.wsum, &tout);
-                /* the scans' barriers order all reads of this chunk before the writes below */
-                if (act && inl) OUT[out_n + w_in + pin] = pix;
-                if (act && !inl) { X[w_out + pout] = px; Y[w_out + pout] = py; Z[w_out + pout] = pz; PIX[w_out + pout] = pix; }
-                w_in += tin; w_out += tout;
+                const unsigned bi = __ballot_sync(0xffffffffu, act && inl), bo = __ballot_sync(0xffffffffu, act && !inl);
+                if (act && inl) { const int q = out_n + w_in + __popc(bi & lt); OUT[q] = pix; OX[q] = px; OY[q] = py; OZ[q] = pz; }
+                if (act && !inl && keep_rest) { const int q = w_out + __popc(bo & lt); X2[q] = px; Y2[q] = py; Z2[q] = pz; PIX2[q] = pix; }
+                w_in += __popc(bi); w_out += __popc(bo);
             }
             if (tid == 0) {
                 SpSegPlane pl;
                 pl.coef[0] = f0; pl.coef[1] = f1; pl.coef[2] = f2; pl.coef[3] = f3;
-                pl.count = w_in; pl.off = off + out_n; pl.cluster = ci; pl.call = call - 1;
+                pl.count = n_inl; pl.off = off + out_n; pl.cluster = ci; pl.call = call - 1;
                 d.seg_planes[s * SP_PSEG + slot] = pl;
             }
-            out_n += w_in; n = w_out;
+            out_n += n_inl; n -= n_inl;
+            { float *t; t = X; X = X2; X2 = t; t = Y; Y = Y2; Y2 = t; t = Z; Z = Z2; Z2 = t; int *u = PIX; PIX = PIX2; PIX2 = u; }
             __syncthreads();
         }
         if (n < rest) break;
@@ -570,107 +646,198 @@ __global__ void k_merge(SpDev d, int nB)
 }
 
 /* ==================================================================================================== */
-/* computeVectorPlaneInfo, StairPerception.cpp:1196-1325: one CTA per merged plane.  The CTA stages the plane's
- * points (chunk chain order) through shared memory; the order-dependent float accumulations are owned by single
- * threads (3 for the centre, 6 for the covariance, 3 for the extents with the reference's else-if rule). */
-#define PS_TILE 1024
-__global__ void __launch_bounds__(256) k_plane_stats(SpDev d)
+/* computeVectorPlaneInfo, StairPerception.cpp:1196-1325: one CTA per merged plane, points streamed (coalesced) from
+ * the plane point lists k_ransac wrote, in chunk-chain order.
+ *   centre, covariance: sequential float sums in point order (the reference's loops) -- warp 0 is the "summer"
+ *     (lane q owns accumulator q: one dependent FADD per point), warps 1.. stage the addends, double-buffered;
+ *   extents: the reference's `if (pj > max) .. else if (pj < min)` scan (:1279-1310) in its exact parallel form:
+ *     max = first occurrence of the largest projection; min = first occurrence of the smallest projection among the
+ *     points that did NOT set a new running maximum (exclusive prefix-max scan + masked arg-min). */
+#define PS_THREADS 256
+#define PS_TILE (PS_THREADS - 32)
+#define PS_E 4                      /* consecutive points per thread in the extent scan */
+struct PsSmem {
+    int ch_start[SP_PSEG + 1], ch_off[SP_PSEG];
+    int nch;
+    float4 stage[2][PS_TILE][2];
+    float acc[6], cen[3], evs[9], evl[3];
+    float wmax[3][PS_THREADS / 32];
+    float carry[3];
+    float rv[6][PS_THREADS / 32]; int ri[6][PS_THREADS / 32];
+    float emn[3], emx[3]; int imn[3], imx[3];
+};
+
+__device__ __forceinline__ int ps_locate(const PsSmem &S, int i, int &c)
 {
-    __shared__ float tx[PS_TILE], ty[PS_TILE], tz[PS_TILE];
-    __shared__ int tp[PS_TILE];
-    __shared__ int ch_start[SP_PSEG + 1], ch_off[SP_PSEG];
-    __shared__ int nch;
-    __shared__ float acc[9], cen[3], evs[9], evl[3];
-    __shared__ float emn[3], emx[3]; __shared__ int imn[3], imx[3];
+    while (c + 1 < S.nch && i >= S.ch_start[c + 1]) ++c;
+    return S.ch_off[c] + (i - S.ch_start[c]);
+}
+
+__global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
+{
+    __shared__ PsSmem S;
     const int s = blockIdx.y, m = blockIdx.x;
     if (m >= d.n_merged[s]) return;
-    const int f = s >> 1, tid = threadIdx.x;
+    const int f = s >> 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const SpMergedPlane mp = d.merged[s * SP_PSEG + m];
     const SpSegPlane *chunks = d.chunks + s * SP_PSEG;
     const int *nxt = d.chunk_next + s * SP_PSEG;
-    const float *X = d.x + (size_t)f * d.N, *Y = d.y + (size_t)f * d.N, *Z = d.z + (size_t)f * d.N;
-    const int *PP = d.plane_pts + (size_t)s * d.N;
+    const size_t base = (size_t)s * d.N;
+    const float *PX = d.plane_x + base, *PY = d.plane_y + base, *PZ = d.plane_z + base;
+    const int *PP = d.plane_pts + base;
     if (tid == 0) {
         int c = mp.head, k = 0, st = 0;
-        while (c >= 0 && k < SP_PSEG) { ch_start[k] = st; ch_off[k] = chunks[c].off; st += chunks[c].count; c = nxt[c]; ++k; }
-        ch_start[k] = st; nch = k;
+        while (c >= 0 && k < SP_PSEG) { S.ch_start[k] = st; S.ch_off[k] = chunks[c].off; st += chunks[c].count; c = nxt[c]; ++k; }
+        S.ch_start[k] = st; S.nch = k;
     }
     __syncthreads();
     const int n = mp.count;
-    auto stage = [&](int t0) {
-        for (int e = tid; e < PS_TILE; e += blockDim.x) {
-            const int i = t0 + e;
-            if (i < n) {
-                int c = 0;
-                while (c + 1 < nch && i >= ch_start[c + 1]) ++c;
-                const int pix = PP[ch_off[c] + (i - ch_start[c])];
-                tx[e] = X[pix]; ty[e] = Y[pix]; tz[e] = Z[pix]; tp[e] = pix;
+    const int ntiles = (n + PS_TILE - 1) / PS_TILE;
+    /* 1. centre, 2. covariance: two summer passes */
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        float acc = 0.f;
+        const int nacc = pass == 0 ? 3 : 6;
+        int cc = 0;
+        for (int t = 0; t <= ntiles; ++t) {
+            if (wid > 0) {
+                const int e = t * PS_TILE + (tid - 32);
+                if (t < ntiles && e < n) {
+                    const int q = ps_locate(S, e, cc);
+                    const float x = PX[q], y = PY[q], z = PZ[q];
+                    float4 *dst = S.stage[t & 1][tid - 32];
+                    if (pass == 0) dst[0] = make_float4(x, y, z, 0.f);
+                    else {
+                        const float px = x - cx, py = y - cy, pz = z - cz;
+                        dst[0] = make_float4(px * px, px * py, px * pz, py * py);
+                        dst[1] = make_float4(py * pz, pz * pz, 0.f, 0.f);
+                    }
+                }
+            } else if (t > 0 && lane < nacc) {
+                const int cnt = min(PS_TILE, n - (t - 1) * PS_TILE);
+                const float *src = reinterpret_cast<const float *>(S.stage[(t - 1) & 1]) + lane;
+                int e = 0;
+                for (; e + 8 <= cnt; e += 8) {
+                    const float v0 = src[(e + 0) * 8], v1 = src[(e + 1) * 8], v2 = src[(e + 2) * 8], v3 = src[(e + 3) * 8];
+                    const float v4 = src[(e + 4) * 8], v5 = src[(e + 5) * 8], v6 = src[(e + 6) * 8], v7 = src[(e + 7) * 8];
+                    acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+                }
+                for (; e < cnt; ++e) acc += src[e * 8];
             }
+            __syncthreads();
         }
-    };
-    /* 1. centre */
-    float a = 0.f;
-    for (int t0 = 0; t0 < n; t0 += PS_TILE) {
-        __syncthreads(); stage(t0); __syncthreads();
-        const int cnt = min(PS_TILE, n - t0);
-        if (tid < 3) { const float *src = tid == 0 ? tx : (tid == 1 ? ty : tz); for (int e = 0; e < cnt; ++e) a += src[e]; }
+        if (wid == 0 && lane < nacc) { if (pass == 0) S.cen[lane] = acc / (float)n; else S.acc[lane] = acc / (float)n; }
+        __syncthreads();
+        if (pass == 0) { cx = S.cen[0]; cy = S.cen[1]; cz = S.cen[2]; }
     }
-    if (tid < 3) cen[tid] = a / (float)n;
-    __syncthreads();
-    const float cx = cen[0], cy = cen[1], cz = cen[2];
-    /* 2. covariance (sequential float), eigen-decomposition */
-    a = 0.f;
-    for (int t0 = 0; t0 < n; t0 += PS_TILE) {
-        __syncthreads(); stage(t0); __syncthreads();
-        const int cnt = min(PS_TILE, n - t0);
-        if (tid < 6) {
-            for (int e = 0; e < cnt; ++e) {
-                const float px = tx[e] - cx, py = ty[e] - cy, pz = tz[e] - cz;
-                float t;
-                switch (tid) { case 0: t = px * px; break; case 1: t = px * py; break; case 2: t = px * pz; break;
-                               case 3: t = py * py; break; case 4: t = py * pz; break; default: t = pz * pz; break; }
-                a += t;
-            }
-        }
-    }
-    if (tid < 6) acc[tid] = a / (float)n;
-    __syncthreads();
     if (tid == 0) {
-        const float cov[9] = { acc[0], acc[1], acc[2], acc[1], acc[3], acc[4], acc[2], acc[4], acc[5] };
+        const float cov[9] = { S.acc[0], S.acc[1], S.acc[2], S.acc[1], S.acc[3], S.acc[4], S.acc[2], S.acc[4], S.acc[5] };
         float ev[3], evc[9];
         det_jacobi3f(cov, ev, evc);
-        for (int j = 0; j < 3; ++j) { evl[j] = ev[j]; for (int k = 0; k < 3; ++k) evs[3 * j + k] = evc[k * 3 + j]; }
+        for (int j = 0; j < 3; ++j) { S.evl[j] = ev[j]; for (int k = 0; k < 3; ++k) S.evs[3 * j + k] = evc[k * 3 + j]; }
+        S.carry[0] = S.carry[1] = S.carry[2] = -FLT_MAX;
     }
     __syncthreads();
-    /* 3. extents along the eigenvectors, with the if / else-if rule of :1279-1310 */
-    float mn = FLT_MAX, mx = -FLT_MAX; int in_ = -1, ix_ = -1;
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-    if (tid < 3) { e0 = evs[3 * tid]; e1 = evs[3 * tid + 1]; e2 = evs[3 * tid + 2]; }
-    for (int t0 = 0; t0 < n; t0 += PS_TILE) {
-        __syncthreads(); stage(t0); __syncthreads();
-        const int cnt = min(PS_TILE, n - t0);
-        if (tid < 3) {
-            for (int e = 0; e < cnt; ++e) {
-                const float px = tx[e] - cx, py = ty[e] - cy, pz = tz[e] - cz;
-                const float pj = px * e0 + (py * e1 + pz * e2);
-                if (pj > mx) { mx = pj; ix_ = tp[e]; }
-                else if (pj < mn) { mn = pj; in_ = tp[e]; }
+    /* 3. extents along the eigenvectors */
+    float ev[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ev[k] = S.evs[k];
+    float bmx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX }, bmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
+    int imx[3] = { -1, -1, -1 }, imn[3] = { -1, -1, -1 };
+    {
+        int cc = 0;
+        for (int t0 = 0; t0 < n; t0 += PS_THREADS * PS_E) {
+            float pj[3][PS_E]; float lm[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            const int e0 = t0 + tid * PS_E;
+#pragma unroll
+            for (int u = 0; u < PS_E; ++u) {
+                const int e = e0 + u;
+                if (e < n) {
+                    const int q = ps_locate(S, e, cc);
+                    const float px = PX[q] - cx, py = PY[q] - cy, pz = PZ[q] - cz;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { pj[a][u] = px * ev[3 * a] + (py * ev[3 * a + 1] + pz * ev[3 * a + 2]); lm[a] = fmaxf(lm[a], pj[a][u]); }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) pj[a][u] = __int_as_float(0x7fc00000);
+                }
             }
+            /* exclusive prefix max over threads (+ carry of the earlier tiles) */
+            float ex[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float inc = lm[a];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = fmaxf(inc, v); }
+                if (lane == 31) S.wmax[a][wid] = inc;
+                float e1 = __shfl_up_sync(0xffffffffu, inc, 1);
+                ex[a] = lane == 0 ? -FLT_MAX : e1;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float pre = S.carry[a];
+                for (int q = 0; q < wid; ++q) pre = fmaxf(pre, S.wmax[a][q]);
+                float run = fmaxf(pre, ex[a]);
+#pragma unroll
+                for (int u = 0; u < PS_E; ++u) {
+                    const float v = pj[a][u];
+                    const int e = e0 + u;
+                    if (v > run) { run = v; if (v > bmx[a]) { bmx[a] = v; imx[a] = e; } }
+                    else if (v < bmn[a]) { bmn[a] = v; imn[a] = e; }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { float c = S.carry[a]; for (int q = 0; q < PS_THREADS / 32; ++q) c = fmaxf(c, S.wmax[a][q]); S.carry[a] = c; }
+            }
+            __syncthreads();
         }
     }
-    if (tid < 3) { emn[tid] = mn; emx[tid] = mx; imn[tid] = in_; imx[tid] = ix_; }
+    /* block reduce: (max value, smallest ordinal) and (min value, smallest ordinal) per axis */
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float v = bmx[a]; int i = imx[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_down_sync(0xffffffffu, v, o); const int i2 = __shfl_down_sync(0xffffffffu, i, o);
+            if (i2 >= 0 && (i < 0 || v2 > v || (v2 == v && i2 < i))) { v = v2; i = i2; }
+        }
+        if (lane == 0) { S.rv[a][wid] = v; S.ri[a][wid] = i; }
+        v = bmn[a]; i = imn[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_down_sync(0xffffffffu, v, o); const int i2 = __shfl_down_sync(0xffffffffu, i, o);
+            if (i2 >= 0 && (i < 0 || v2 < v || (v2 == v && i2 < i))) { v = v2; i = i2; }
+        }
+        if (lane == 0) { S.rv[3 + a][wid] = v; S.ri[3 + a][wid] = i; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        const bool is_max = tid < 3;
+        float v = is_max ? -FLT_MAX : FLT_MAX; int i = -1;
+        for (int q = 0; q < PS_THREADS / 32; ++q) {
+            const float v2 = S.rv[tid][q]; const int i2 = S.ri[tid][q];
+            if (i2 >= 0 && (i < 0 || (is_max ? v2 > v : v2 < v) || (v2 == v && i2 < i))) { v = v2; i = i2; }
+        }
+        int cc = 0;
+        const int pix = i >= 0 ? PP[ps_locate(S, i, cc)] : -1;
+        if (is_max) { S.emx[tid] = v; S.imx[tid] = pix; } else { S.emn[tid - 3] = v; S.imn[tid - 3] = pix; }
+    }
     __syncthreads();
     if (tid == 0) {
+        const float *X = d.x + (size_t)f * d.N, *Y = d.y + (size_t)f * d.N, *Z = d.z + (size_t)f * d.N;
         sp_plane_record r;
         r.type = (s & 1) ? 0 : 1; r.ptype = 3; r.count = n; r.first = 0;
         const float qnan = __int_as_float(0x7fc00000);
         for (int k = 0; k < 4; ++k) r.coef[k] = mp.coef[k];
-        for (int k = 0; k < 3; ++k) { r.center[k] = cen[k]; r.eval[k] = evl[k]; r.pmin[k] = emn[k]; r.pmax[k] = emx[k]; r.idx_min[k] = imn[k]; r.idx_max[k] = imx[k]; }
-        for (int k = 0; k < 9; ++k) r.evec[k] = evs[k];
+        for (int k = 0; k < 3; ++k) { r.center[k] = S.cen[k]; r.eval[k] = S.evl[k]; r.pmin[k] = S.emn[k]; r.pmax[k] = S.emx[k]; r.idx_min[k] = S.imn[k]; r.idx_max[k] = S.imx[k]; }
+        for (int k = 0; k < 9; ++k) r.evec[k] = S.evs[k];
         for (int a2 = 0; a2 < 3; ++a2) {
             for (int k = 0; k < 3; ++k) { r.pt_min[a2][k] = qnan; r.pt_max[a2][k] = qnan; }
-            if (imn[a2] >= 0) { r.pt_min[a2][0] = X[imn[a2]]; r.pt_min[a2][1] = Y[imn[a2]]; r.pt_min[a2][2] = Z[imn[a2]]; }
-            if (imx[a2] >= 0) { r.pt_max[a2][0] = X[imx[a2]]; r.pt_max[a2][1] = Y[imx[a2]]; r.pt_max[a2][2] = Z[imx[a2]]; }
+            if (S.imn[a2] >= 0) { r.pt_min[a2][0] = X[S.imn[a2]]; r.pt_min[a2][1] = Y[S.imn[a2]]; r.pt_min[a2][2] = Z[S.imn[a2]]; }
+            if (S.imx[a2] >= 0) { r.pt_max[a2][0] = X[S.imx[a2]]; r.pt_max[a2][1] = Y[S.imx[a2]]; r.pt_max[a2][2] = Z[S.imx[a2]]; }
         }
         for (int k = 0; k < 3; ++k) r.pcenter[k] = (r.pt_max[0][k] + r.pt_min[0][k]) / 2;
         d.info[s * SP_PSEG + m] = r;
