@@ -116,34 +116,63 @@ __device__ __forceinline__ void sp_uf_unite(int *parent, int a, int b)
 /* One thread per point in bucket-major order.  Every unordered pair of points in adjacent cells is tested exactly
  * once: own cell against members with a smaller list position, plus the 13 "forward" neighbour cells.  (Two cells
  * sharing a bucket only cause repeated, idempotent unions.)  Union-find is indexed by list position, so a
- * component's root is its smallest member position whatever the visiting order. */
+ * component's root is its smallest member position whatever the visiting order.
+ * The distance tests run warp-converged; the edges they find are pushed to a per-warp queue and united 32 at a
+ * time, so the (divergent, pointer-chasing) union-find code always runs with a full warp. */
 __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
 {
+    __shared__ int2 queue[8][64];
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = (size_t)s * d.N;
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     int *parent = d.parent + base;
     const float4 *sp = d.spts + base;
     const float cell = d.c.cell, r2 = d.c.r2;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const float4 p = sp[t];
-        const int oi = __float_as_int(p.w);
-        int a, b, c;
-        const unsigned h0 = sp_point_bucket(p, cell, a, b, c);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int2 *q = queue[wid];
+    int qn = 0;                                                          /* warp-uniform */
+    for (int t0 = blockIdx.x * blockDim.x + wid * 32; t0 < n; t0 += gridDim.x * blockDim.x) {
+        const int t = t0 + lane;
+        const bool act = t < n;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        int oi = 0, a = 0, b = 0, c = 0; unsigned h0 = 0;
+        if (act) { p = sp[t]; oi = __float_as_int(p.w); h0 = sp_point_bucket(p, cell, a, b, c); }
         for (int k = 13; k < 27; ++k) {                                  /* offsets (0,0,0) then the 13 forward ones */
-            const int da = k / 9 - 1, db = (k / 3) % 3 - 1, dc = k % 3 - 1;
-            const unsigned h = k == 13 ? h0 : (sp_cell_hash(a + da, b + db, c + dc) & ((1u << SP_HASH_BITS) - 1u));
-            const int j1 = start[h + 1];
-            for (int j = start[h]; j < j1; ++j) {
-                const float4 q = sp[j];
-                const int oj = __float_as_int(q.w);
-                if (k == 13 && oj >= oi) continue;
-                const float d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
-                float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
-                if (dist < r2 && parent[oi] != parent[oj]) sp_uf_unite(parent, oi, oj);
+            int j = 0, j1 = 0;
+            if (act) {
+                const int da = k / 9 - 1, db = (k / 3) % 3 - 1, dc = k % 3 - 1;
+                const unsigned h = k == 13 ? h0 : (sp_cell_hash(a + da, b + db, c + dc) & ((1u << SP_HASH_BITS) - 1u));
+                j = start[h]; j1 = start[h + 1];
+            }
+            while (__any_sync(0xffffffffu, j < j1)) {
+                bool hit = false; int oj = 0;
+                if (j < j1) {
+                    const float4 qq = sp[j];
+                    oj = __float_as_int(qq.w);
+                    const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
+                    float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
+                    hit = dist < r2 && !(k == 13 && oj >= oi);
+                    if (hit) hit = parent[oi] != parent[oj];
+                    ++j;
+                }
+                const unsigned bm = __ballot_sync(0xffffffffu, hit);
+                if (bm) {
+                    if (hit) q[qn + __popc(bm & lt)] = make_int2(oi, oj);
+                    qn += __popc(bm);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        const int2 e = q[qn - 32 + lane];
+                        qn -= 32;
+                        __syncwarp();
+                        sp_uf_unite(parent, e.x, e.y);
+                    }
+                }
             }
         }
     }
+    __syncwarp();
+    if (lane < qn) { const int2 e = q[lane]; sp_uf_unite(parent, e.x, e.y); }
 }
 
 __global__ void __launch_bounds__(256) k_cl_flatten(SpDev d)
