@@ -147,6 +147,12 @@ const char *sp_stage_name(int i);
 /* number of kernels this library launched since sp_create (its own + CUB) */
 int64_t sp_launch_count(const sp_ctx *ctx);
 
+/* Normal estimation mode.  0 (default) = organised-image normals, the live path (normalEstimationIntegral,
+ * StairPerception.cpp:579-592).  1 = k-nearest-neighbour covariance normals for unorganised clouds (normalEstimationOMP,
+ * StairPerception.cpp:524-541) with k = ParameterDef::normal_compute_points (<= 128); create the context with
+ * width = number of points, height = 1.  Query = search surface = every finite point of the frame. */
+int sp_set_normal_mode(sp_ctx *ctx, int mode);
+
 /* Per-kernel trace of the last chunk (the reference's TIME_RECORD per-stage timers, StairPerception.hpp:13,181-190,
  * at kernel granularity).  Off by default; sp_set_trace(ctx, 1) or the environment variable SP_TRACE=1 makes the
  * library record a CUDA event after every launch.  sp_trace_ms(ctx, -1, 0, 0) returns the number of entries;

@@ -107,7 +107,7 @@ class Oracle:
     def __del__(self):
         self.close()
 
-    def process(self, cloud, width, height, R=None, show_mode=10, keep_taps=True):
+    def process(self, cloud, width, height, R=None, show_mode=10, keep_taps=True, normal_mode=0):
         """cloud: (N,4) float32/uint32 view or raw bytes of N x 16 B records.  Returns number of planes."""
         buf = np.ascontiguousarray(cloud)
         assert buf.nbytes == width * height * 16
@@ -115,7 +115,7 @@ class Oracle:
         if R is not None:
             R = np.ascontiguousarray(R, dtype=np.float32)
             Rp = R.ctypes.data
-        return self.L.orc_process(self.h, buf.ctypes.data, width, height, Rp, show_mode, 0, 1 if keep_taps else 0)
+        return self.L.orc_process(self.h, buf.ctypes.data, width, height, Rp, show_mode, normal_mode, 1 if keep_taps else 0)
 
     def tap_names(self):
         n = self.L.orc_tap_names(self.h, None, 0)

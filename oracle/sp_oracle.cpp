@@ -50,6 +50,7 @@ struct orc_ctx {
     int normal_arith = 1;    /* 0 = PCL integral images (double), 1 = fixed-order double box sums */
     int voxel_order = 0;     /* 0 = stable, 1 = std::sort on the key only */
     int eig_math = 0;        /* 0 = portable det_* math, 1 = libm */
+    int knn_threads = 8;     /* host threads of the kNN normal search (a3') */
     int acos_float = 0;      /* a8: 0 = acos((double)nx), 1 = (double)acosf(nx)  (overload ambiguity) */
     std::map<std::string, Tap> taps;
     double stage_ms[ST_COUNT];
@@ -225,6 +226,109 @@ void normals_integral(orc_ctx *c)
             if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
             c->nx[i] = fx; c->ny[i] = fy; c->nz[i] = fz;
         }
+}
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* a3': normalEstimationOMP (StairPerception.cpp:524-541) -> pcl::NormalEstimationOMP, k-nearest-neighbour search
+ * (upstream features/impl/normal_3d_omp.hpp, features/normal_3d.h, common/impl/centroid.hpp, common/impl/eigen.hpp).
+ * Query = search surface = every finite point of the frame.  Neighbours: the k points with the smallest
+ * flann::L2_Simple squared distance (sequential float sum of squared differences), in ascending (distance, index)
+ * order -- FLANN's order on distance ties is unspecified; the index tie-break is this oracle's rule.  The exact
+ * search runs on a uniform grid with shell expansion (any exact method gives the same list). */
+void normals_knn(orc_ctx *c, int k, int nthreads)
+{
+    const int N = c->N;
+    const float *X = c->x.data(), *Y = c->y.data(), *Z = c->z.data();
+    c->nx.assign(N, kNaN); c->ny.assign(N, kNaN); c->nz.assign(N, kNaN);
+    std::vector<int> valid; valid.reserve(N);
+    float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int i = 0; i < N; ++i)
+        if (finite3(X[i], Y[i], Z[i])) {
+            valid.push_back(i);
+            mn[0] = std::min(mn[0], X[i]); mx[0] = std::max(mx[0], X[i]);
+            mn[1] = std::min(mn[1], Y[i]); mx[1] = std::max(mx[1], Y[i]);
+            mn[2] = std::min(mn[2], Z[i]); mx[2] = std::max(mx[2], Z[i]);
+        }
+    const int n = (int)valid.size();
+    if (n == 0 || k < 1) return;
+    const double ex = (double)mx[0] - mn[0], ey = (double)mx[1] - mn[1], ez = (double)mx[2] - mn[2];
+    double h = sqrt(std::max(1e-12, (ex * ey + ey * ez + ex * ez) * k / (3.14159265358979 * n)));
+    h = std::max(h, 1e-4);
+    const int gx = std::min(1024, (int)(ex / h) + 1), gy = std::min(1024, (int)(ey / h) + 1), gz = std::min(1024, (int)(ez / h) + 1);
+    const double hx = ex / gx + 1e-9, hy = ey / gy + 1e-9, hz = ez / gz + 1e-9;       /* actual cell edges */
+    auto cell_of = [&](int i, int &a, int &b, int &d) {
+        a = std::min(gx - 1, std::max(0, (int)(((double)X[i] - mn[0]) / hx)));
+        b = std::min(gy - 1, std::max(0, (int)(((double)Y[i] - mn[1]) / hy)));
+        d = std::min(gz - 1, std::max(0, (int)(((double)Z[i] - mn[2]) / hz)));
+    };
+    std::vector<int> cstart((size_t)gx * gy * gz + 1, 0), order(n);
+    for (int i : valid) { int a, b, d; cell_of(i, a, b, d); ++cstart[((size_t)d * gy + b) * gx + a + 1]; }
+    for (size_t q = 1; q < cstart.size(); ++q) cstart[q] += cstart[q - 1];
+    { std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+      for (int i : valid) { int a, b, d; cell_of(i, a, b, d); order[fill[((size_t)d * gy + b) * gx + a]++] = i; } }
+    const double hmin = std::min(hx, std::min(hy, hz));
+    auto work = [&](int lo, int hi) {
+        std::vector<std::pair<float, int>> cand;
+        for (int vi = lo; vi < hi; ++vi) {
+            const int i = valid[vi];
+            int a, b, d; cell_of(i, a, b, d);
+            const int want = std::min(k, n);
+            cand.clear();
+            for (int shell = 0;; ++shell) {
+                for (int dz = -shell; dz <= shell; ++dz) for (int dy = -shell; dy <= shell; ++dy) for (int dx = -shell; dx <= shell; ++dx) {
+                    if (std::max(std::abs(dx), std::max(std::abs(dy), std::abs(dz))) != shell) continue;
+                    const int ca = a + dx, cb = b + dy, cd = d + dz;
+                    if (ca < 0 || cb < 0 || cd < 0 || ca >= gx || cb >= gy || cd >= gz) continue;
+                    const size_t cell = ((size_t)cd * gy + cb) * gx + ca;
+                    for (int q = cstart[cell]; q < cstart[cell + 1]; ++q) {
+                        const int j = order[q];
+                        const float d0 = X[i] - X[j], d1 = Y[i] - Y[j], d2 = Z[i] - Z[j];
+                        float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;
+                        cand.push_back({ dist, j });
+                    }
+                }
+                const bool all = shell >= std::max(gx, std::max(gy, gz));
+                if ((int)cand.size() >= want || all) {
+                    std::sort(cand.begin(), cand.end());
+                    if (all) break;
+                    if ((int)cand.size() >= want) {
+                        const double reach = shell * hmin * (1.0 - 1e-6);                /* everything nearer than this has been seen */
+                        if ((double)cand[want - 1].first < reach * reach) break;
+                    }
+                }
+            }
+            const int cnt = std::min((int)cand.size(), want);
+            /* computeMeanAndCovarianceMatrix (float, single pass, neighbour order) + solvePlaneParameters */
+            float accu[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            for (int q = 0; q < cnt; ++q) {
+                const int j = cand[q].second;
+                const float px = X[j], py = Y[j], pz = Z[j];
+                accu[0] += px * px; accu[1] += px * py; accu[2] += px * pz;
+                accu[3] += py * py; accu[4] += py * pz; accu[5] += pz * pz;
+                accu[6] += px; accu[7] += py; accu[8] += pz;
+            }
+            const float fc = (float)cnt;
+            for (int q = 0; q < 9; ++q) accu[q] = accu[q] / fc;
+            float cov[9];
+            cov[0] = accu[0] - accu[6] * accu[6]; cov[1] = accu[1] - accu[6] * accu[7]; cov[2] = accu[2] - accu[6] * accu[8];
+            cov[4] = accu[3] - accu[7] * accu[7]; cov[5] = accu[4] - accu[7] * accu[8]; cov[8] = accu[5] - accu[8] * accu[8];
+            cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+            float ev, evec[3];
+            if (c->eig_math) det_eigen33f<1>(cov, &ev, evec); else det_eigen33f<0>(cov, &ev, evec);
+            float fx = evec[0], fy = evec[1], fz = evec[2];
+            const float vx = 0.0f - X[i], vy = 0.0f - Y[i], vz = 0.0f - Z[i];
+            const float cs = (vx * fx + vy * fy + vz * fz);
+            if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
+            c->nx[i] = fx; c->ny[i] = fy; c->nz[i] = fz;
+        }
+    };
+    nthreads = std::max(1, std::min(nthreads, 64));
+    if (nthreads == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(work, (int)((int64_t)n * t / nthreads), (int)((int64_t)n * (t + 1) / nthreads));
+        for (auto &t : th) t.join();
+    }
 }
 
 /* ---------------------------------------------------------------------------------------------------- */
@@ -679,6 +783,7 @@ int orc_set_mode(orc_ctx *c, const char *name, int value)
     else if (n == "voxel_order") c->voxel_order = value;
     else if (n == "eig_math") c->eig_math = value;
     else if (n == "acos_float") c->acos_float = value;
+    else if (n == "knn_threads") c->knn_threads = value;
     else return -1;
     return 0;
 }
@@ -686,7 +791,6 @@ int orc_set_mode(orc_ctx *c, const char *name, int value)
 int orc_process(orc_ctx *c, const void *xyzrgba, int width, int height, const float *R9, int show_mode, int normal_mode, int keep_taps)
 {
     if (!c || !xyzrgba || width <= 0 || height <= 0) return -1;
-    if (normal_mode != 0) return -2;   /* kNN normals (a3') not restated yet */
     c->taps.clear(); c->records.clear(); c->plane_idx.clear(); c->rand_pos = 0;
     memset(c->stage_ms, 0, sizeof(c->stage_ms));
     c->W = width; c->H = height; c->N = width * height;
@@ -697,7 +801,8 @@ int orc_process(orc_ctx *c, const void *xyzrgba, int width, int height, const fl
     double t0 = now_ms(), t1;
     level_and_mask(c, (const uint8_t *)xyzrgba, R9);
     t1 = now_ms(); c->stage_ms[ST_LEVEL] = t1 - t0; t0 = t1;
-    normals_integral(c);
+    if (normal_mode == 0) normals_integral(c);
+    else normals_knn(c, c->p.normal_compute_points, c->knn_threads);
     t1 = now_ms(); c->stage_ms[ST_NORMALS] = t1 - t0; t0 = t1;
     if (keep_taps) {
         std::vector<float> xyz((size_t)c->N * 3), nrm((size_t)c->N * 3);

@@ -67,6 +67,7 @@ def lib():
         L.sp_launch_count.restype = C.c_int64
         L.sp_launch_count.argtypes = [C.c_void_p]
         L.sp_run_stage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sp_set_normal_mode.argtypes = [C.c_void_p, C.c_int]
         L.sp_set_trace.argtypes = [C.c_void_p, C.c_int]
         L.sp_trace_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
         L.sp_stream.restype = C.c_void_p
@@ -191,6 +192,10 @@ class Context:
         arr = (C.c_float * 16)()
         n = self.L.sp_stage_ms(self.h, arr, 16)
         return {self.L.sp_stage_name(i).decode(): float(arr[i]) for i in range(n)}
+
+    def set_normal_mode(self, mode):
+        """0 = organised-image normals (live path), 1 = kNN covariance normals for unorganised clouds (a3')"""
+        self._check(self.L.sp_set_normal_mode(self.h, int(mode)), "sp_set_normal_mode")
 
     def set_trace(self, on=True):
         self.L.sp_set_trace(self.h, 1 if on else 0)

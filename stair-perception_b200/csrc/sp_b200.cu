@@ -5,6 +5,7 @@
 #include "sp_common.cuh"
 #include "sp_front.cuh"
 #include "sp_seg.cuh"
+#include "sp_knn.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -111,6 +112,11 @@ struct sp_ctx {
     cudaEvent_t ev_in[2], ev_done[2];
     float stage_ms[STG_COUNT];
     /* per-kernel trace of the last chunk (SP_TRACE=1 or sp_set_trace): one event after every launch */
+    /* a3' kNN normals (unorganised clouds): allocated on first use */
+    int normal_mode = 0;
+    int *knn_mm = nullptr, *knn_bstart = nullptr, *knn_bend = nullptr;
+    SpKnnGrid *knn_grid = nullptr;
+    float4 *knn_pts = nullptr;
     bool trace = false;
     std::vector<cudaEvent_t> tev;
     std::vector<const char *> tname;
@@ -160,13 +166,34 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     const bool all = only_stage < 0 || only_stage == 2;
     mark(ctx, "begin");
     CK(cudaEventRecord(ctx->ev[0], st));
-    if (all || only_stage == 0) {
+    if ((all || only_stage == 0) && ctx->normal_mode == 0) {
         k_init_frames<<<(nB * SP_NCOUNT + 255) / 256, 256, 0, st>>>(d, nB);
         mark(ctx, "k_init_frames");
         dim3 g((ctx->W + K1_TW - 1) / K1_TW, (ctx->H + K1_TH - 1) / K1_TH, nB);
         k_ingest_normals<<<g, K1_THREADS, sizeof(K1Smem), st>>>(d);
         mark(ctx, "k_ingest_normals");
         ctx->launches += 2;
+    } else if (all || only_stage == 0) {
+        /* a3': unorganised cloud, kNN covariance normals */
+        const int k = std::max(1, std::min(ctx->params.normal_compute_points, KNN_CAP));
+        const int gx = std::min(d.nblk, 148 * 8);
+        k_init_frames<<<(nB * SP_NCOUNT + 255) / 256, 256, 0, st>>>(d, nB);
+        k_knn_init<<<(nB * 8 + 255) / 256, 256, 0, st>>>(ctx->knn_mm, nB);
+        k_ingest_plain<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_mm);
+        mark(ctx, "k_ingest_plain");
+        k_knn_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, ctx->knn_mm, ctx->knn_grid, k, nB);
+        k_knn_key<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_grid);
+        mark(ctx, "k_knn_key");
+        size_t tb = ctx->cub_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)nB * N, 0, 32 + frame_bits(nB), st));
+        mark(ctx, "knn_radix_sort");
+        CK(cudaMemsetAsync(ctx->knn_bstart, 0, sizeof(int) * ((size_t)nB << KNN_BITS), st));
+        CK(cudaMemsetAsync(ctx->knn_bend, 0, sizeof(int) * ((size_t)nB << KNN_BITS), st));
+        k_knn_starts<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_bstart, ctx->knn_bend, ctx->knn_pts);
+        mark(ctx, "k_knn_starts");
+        k_knn_normals<<<dim3(148 * 8, nB), KNN_WARPS * 32, 0, st>>>(d, ctx->knn_grid, ctx->knn_bstart, ctx->knn_bend, ctx->knn_pts, k);
+        mark(ctx, "k_knn_normals");
+        ctx->launches += 7 + 2 + (32 + frame_bits(nB) + 7) / 8;
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
@@ -457,6 +484,26 @@ int sp_stage_ms(sp_ctx *ctx, float *out, int cap)
     return n;
 }
 const char *sp_stage_name(int i) { return (i >= 0 && i < STG_COUNT) ? kStageNames[i] : ""; }
+
+int sp_set_normal_mode(sp_ctx *ctx, int mode)
+{
+    if (!ctx || (mode != 0 && mode != 1)) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (mode == 1 && !ctx->knn_pts) {
+        const size_t B = ctx->B, N = ctx->N;
+        cudaError_t e;
+        if ((e = dalloc(ctx, &ctx->knn_mm, B * 8)) != cudaSuccess || (e = dalloc(ctx, &ctx->knn_grid, B)) != cudaSuccess ||
+            (e = dalloc(ctx, &ctx->knn_bstart, B << KNN_BITS)) != cudaSuccess || (e = dalloc(ctx, &ctx->knn_bend, B << KNN_BITS)) != cudaSuccess ||
+            (e = dalloc(ctx, &ctx->knn_pts, B * N)) != cudaSuccess) {
+            ctx->err = std::string("cudaMalloc (kNN workspaces): ") + cudaGetErrorString(e);
+            ctx->knn_pts = nullptr;
+            return SP_ERR_CUDA;
+        }
+    }
+    ctx->normal_mode = mode;
+    return SP_OK;
+}
 
 void sp_set_trace(sp_ctx *ctx, int on) { if (ctx) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->trace = on != 0; ctx->tn = 0; } }
 

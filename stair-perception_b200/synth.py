@@ -104,3 +104,37 @@ def make_batch(n, first_id=0, **kw):
         recs.append(r)
         Rs.append(R)
     return np.stack(recs), np.stack(Rs)
+
+
+def make_dense_scene(n_points=2_000_000, seed=0, rise=0.11, run=0.28, width=1.0, n_steps=4, sigma=0.002, invalid_frac=0.01):
+    """BASELINE.json config 4: an UNORGANISED dense stair scene, already levelled (+x down, +y forward, +z lateral).
+    Points are sampled uniformly (by area) on ground, treads, risers, the landing and a back wall, with isotropic
+    Gaussian noise `sigma`; `invalid_frac` of them get rgba = 0 (validity mask).  Returns records[n_points] {x,y,z,rgba};
+    use it with a context of width = n_points, height = 1 and normal mode 1 (kNN normals, a3')."""
+    rng = np.random.default_rng(424242 + int(seed))
+    cam_h, y0, hw = 0.95, 0.9, width / 2
+    rects = []          # (origin, edge u, edge v)
+    rects.append((np.array([cam_h, 0.3, -1.0]), np.array([0, y0 - 0.3, 0]), np.array([0, 0, 2.0])))                 # ground
+    for i in range(1, n_steps + 1):
+        ylo = y0 + (i - 1) * run
+        depth = run if i < n_steps else run + 1.0                                                                      # last tread = landing
+        rects.append((np.array([cam_h - i * rise, ylo, -hw]), np.array([0, depth, 0]), np.array([0, 0, width])))      # tread
+        rects.append((np.array([cam_h - i * rise, ylo, -hw]), np.array([rise, 0, 0]), np.array([0, 0, width])))       # riser
+    yb = y0 + n_steps * run + 1.0
+    rects.append((np.array([cam_h - n_steps * rise - 1.0, yb, -hw]), np.array([1.0, 0, 0]), np.array([0, 0, width])))  # back wall
+    areas = np.array([np.linalg.norm(np.cross(u, v)) for _, u, v in rects])
+    which = rng.choice(len(rects), size=n_points, p=areas / areas.sum())
+    a, b = rng.random(n_points), rng.random(n_points)
+    O = np.stack([r[0] for r in rects])[which]
+    U = np.stack([r[1] for r in rects])[which]
+    V = np.stack([r[2] for r in rects])[which]
+    P = O + a[:, None] * U + b[:, None] * V + rng.normal(0.0, sigma, size=(n_points, 3))
+    rec = np.zeros(n_points, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])
+    rec["x"], rec["y"], rec["z"] = P[:, 0], P[:, 1], P[:, 2]
+    rgb = rng.integers(1, 256, size=(n_points, 3), dtype=np.uint32)
+    rgba = (np.uint32(255) << 24) | (rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2]
+    rec["rgba"] = np.where(rng.random(n_points) < invalid_frac, 0, rgba).astype(np.uint32)
+    return rec
+
+
+DENSE_PARAMS = {"voxel_x": 0.005, "voxel_y": 0.005, "voxel_z": 0.005}     # config 4: fine leaf (the GUI minimum is 0.01)

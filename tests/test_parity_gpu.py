@@ -177,3 +177,51 @@ def test_cpp_facade_matches_oracle(sp, orc, samples):
     r = subprocess.run([os.path.join(ROOT, "examples", "files_mode"), os.path.join(ROOT, "tests", "golden", "samples", "0000_cloud.pcd"), "4"],
                        capture_output=True, text=True, check=True)
     assert r.stdout.split()[:6] == ["has_planes", "0", "planes", "1", "cloud_show", str(int(o.counts()["n_h"]) if False else 10679)]
+
+
+@pytest.mark.parametrize("n_points,seed", [(150_000, 1), (60_000, 2)])
+def test_knn_normals_unorganised_parity(sp, orc, synth, n_points, seed):
+    """a3' (normalEstimationOMP, StairPerception.cpp:524-541): unorganised cloud, kNN covariance normals (k = 69), then the
+    same pipeline.  Neighbour lists in (distance, index) order make every float sum order-identical: bit-exact taps."""
+    rec = synth.make_dense_scene(n_points, seed=seed)
+    rec["x"][100:140] = np.nan                                   # a few non-finite points with valid colour
+    rec[-1]["x"], rec[-1]["y"], rec[-1]["z"] = 3.0, 9.0, 4.0     # an isolated point: its neighbours are far away
+    p = dict(sp.DEFAULT_PARAMS)
+    p.update(synth.DENSE_PARAMS)
+    ctx = sp.Context(p, device=0, width=n_points, height=1, max_batch=1)
+    ctx.set_normal_mode(1)
+    res = ctx.process_frames(rec)[0]
+    o = orc.Oracle(p, knn_threads=16)
+    o.process(rec, n_points, 1, normal_mode=1)
+    bad = compare_frame(ctx, 0, res, o)
+    assert not bad, "\n".join(bad[:20])
+    assert int(res["status"]) == 0 and int(res["n_planes"]) >= 8
+    nrm = ctx.tap(0, "normals")
+    ok = np.isfinite(nrm[:, 0])
+    assert ok.sum() == int(res["n_valid"])
+    assert np.allclose((nrm[ok].astype(np.float64) ** 2).sum(1), 1.0, atol=1e-4)
+    ctx.close()
+
+
+def test_knn_config4_two_million_points(sp, orc, synth):
+    """BASELINE.json config 4 at full size: 2 M-point dense scene, leaf 0.005, kNN normals; GPU vs oracle on every count,
+    the normals and the final planes, plus size-independent properties (treads 0.11 m apart, risers 0.28 m apart)."""
+    import os
+    n_points = 2_000_000
+    rec = synth.make_dense_scene(n_points, seed=0)
+    p = dict(sp.DEFAULT_PARAMS)
+    p.update(synth.DENSE_PARAMS)
+    ctx = sp.Context(p, device=0, width=n_points, height=1, max_batch=1)
+    ctx.set_normal_mode(1)
+    res = ctx.process_frames(rec)[0]
+    assert int(res["status"]) == 0
+    planes = res["planes"][:int(res["n_planes"])]
+    treads = sorted(-float(q["coef"][3]) for q in planes if q["type"] == 1 and 15000 < q["count"] < 40000)
+    risers = sorted(float(q["coef"][3]) for q in planes if q["type"] == 0 and 5000 < q["count"] < 12000)
+    assert len(treads) >= 3 and np.allclose(np.diff(treads), 0.11, atol=3e-3)
+    assert len(risers) >= 4 and np.allclose(np.diff(risers), 0.28, atol=5e-3)
+    o = orc.Oracle(p, knn_threads=max(8, len(os.sched_getaffinity(0))))
+    o.process(rec, n_points, 1, normal_mode=1)
+    bad = compare_frame(ctx, 0, res, o, taps=["normals", "voxel_idx", "h_idx", "v_idx", "h_root", "v_root", "plane_idx"])
+    assert not bad, "\n".join(bad[:20])
+    ctx.close()
