@@ -141,6 +141,13 @@ int64_t sp_tap_copy(sp_ctx *ctx, int frame, const char *name, void *dst, int64_t
  * of frame `frame` of the last chunk, in the reference's point order.  Either output may be NULL. */
 int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t *pixel_idx, int cap);
 
+/* Replaces StairDetection::findMinMaxProjPoint (StairPerception.cpp:2780-2808), which the stair model calls on hand-off
+ * planes (:2680, :2695, :2698, :2888, :2951, :2986, :3053): the points of plane `plane` (frame `frame` of the last chunk)
+ * whose projection of (p - centre) on `dir3` is largest / smallest, reduced on the device so the plane's cloud never has
+ * to travel.  center3 = NULL uses the plane's own centre.  Outputs may be NULL; xyz = NaN and pixel = -1 for an empty plane. */
+int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
+                   int32_t *max_pixel, int32_t *min_pixel);
+
 /* Timing of the last chunk: CUDA-event milliseconds per stage; returns number of stages written. */
 int sp_stage_ms(sp_ctx *ctx, float *out, int cap);
 const char *sp_stage_name(int i);

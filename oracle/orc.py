@@ -78,6 +78,7 @@ def lib():
         L.orc_rotation_from_quat.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_mt19937_draws.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_minmax_proj.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_eigen33.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_jacobi3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -138,6 +139,16 @@ class Oracle:
         if name.endswith("_log"):
             out = out.reshape(-1, 10)
         return out
+
+    def minmax_proj(self, plane, direction, center=None):
+        dv = np.ascontiguousarray(direction, dtype=np.float32)
+        cv = None if center is None else np.ascontiguousarray(center, dtype=np.float32)
+        mx, mn = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        pm, pn = C.c_int32(), C.c_int32()
+        rc = self.L.orc_minmax_proj(self.h, plane, None if cv is None else cv.ctypes.data, dv.ctypes.data, mx.ctypes.data, mn.ctypes.data,
+                                    C.byref(pm), C.byref(pn))
+        assert rc == 0
+        return mx, mn, int(pm.value), int(pn.value)
 
     def counts(self):
         return dict(zip(COUNT_NAMES, self.tap("counts").tolist()))

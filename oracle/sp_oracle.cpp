@@ -987,4 +987,26 @@ void orc_glibc_rand(uint32_t seed, int n, int32_t *out) { glibc_rand_stream(seed
 void orc_eigen33(const float *cov9, int libm, float *ev, float *evec) { if (libm) det_eigen33f<1>(cov9, ev, evec); else det_eigen33f<0>(cov9, ev, evec); }
 void orc_jacobi3(const float *cov9, float *evals3, float *evecs9) { det_jacobi3f(cov9, evals3, evecs9); }
 
+/* findMinMaxProjPoint, StairPerception.cpp:2780-2808, on plane `plane` of the last frame processed */
+int orc_minmax_proj(orc_ctx *c, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz, int32_t *max_pixel, int32_t *min_pixel)
+{
+    if (!c || plane < 0 || plane >= (int)c->records.size() || !dir3) return -1;
+    const orc_plane_record &r = c->records[plane];
+    const float *cen = center3 ? center3 : r.center;
+    float max_proj = -FLT_MAX, min_proj = FLT_MAX; int imax = -1, imin = -1;
+    for (int i = 0; i < r.count; ++i) {
+        const int pix = c->plane_idx[r.first + i];
+        const float px = c->x[pix] - cen[0], py = c->y[pix] - cen[1], pz = c->z[pix] - cen[2];
+        const float proj = dir3[0] * px + (dir3[1] * py + dir3[2] * pz);      /* Eigen's unrolled 3-term reduction */
+        if (proj > max_proj) { max_proj = proj; imax = pix; }
+        if (proj < min_proj) { min_proj = proj; imin = pix; }
+    }
+    for (int k = 0; k < 3; ++k) { if (max_xyz) max_xyz[k] = kNaN; if (min_xyz) min_xyz[k] = kNaN; }
+    if (imax >= 0 && max_xyz) { max_xyz[0] = c->x[imax]; max_xyz[1] = c->y[imax]; max_xyz[2] = c->z[imax]; }
+    if (imin >= 0 && min_xyz) { min_xyz[0] = c->x[imin]; min_xyz[1] = c->y[imin]; min_xyz[2] = c->z[imin]; }
+    if (max_pixel) *max_pixel = imax;
+    if (min_pixel) *min_pixel = imin;
+    return 0;
+}
+
 } /* extern "C" */

@@ -67,6 +67,7 @@ def lib():
         L.sp_launch_count.restype = C.c_int64
         L.sp_launch_count.argtypes = [C.c_void_p]
         L.sp_run_stage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sp_minmax_proj.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sp_set_normal_mode.argtypes = [C.c_void_p, C.c_int]
         L.sp_set_trace.argtypes = [C.c_void_p, C.c_int]
         L.sp_trace_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
@@ -187,6 +188,16 @@ class Context:
         idx = np.empty(count, dtype=np.int32)
         n = self._check(self.L.sp_copy_plane_points(self.h, frame, plane, xyz.ctypes.data, idx.ctypes.data, count), "sp_copy_plane_points")
         return xyz[:n], idx[:n]
+
+    def minmax_proj(self, frame, plane, direction, center=None):
+        """findMinMaxProjPoint on the device: returns (max_xyz, min_xyz, max_pixel, min_pixel)"""
+        dv = np.ascontiguousarray(direction, dtype=np.float32)
+        cv = None if center is None else np.ascontiguousarray(center, dtype=np.float32)
+        mx, mn = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        pm, pn = C.c_int32(), C.c_int32()
+        self._check(self.L.sp_minmax_proj(self.h, frame, plane, None if cv is None else cv.ctypes.data, dv.ctypes.data, mx.ctypes.data,
+                                          mn.ctypes.data, C.byref(pm), C.byref(pn)), "sp_minmax_proj")
+        return mx, mn, int(pm.value), int(pn.value)
 
     def stage_ms(self):
         arr = (C.c_float * 16)()

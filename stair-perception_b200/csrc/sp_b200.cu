@@ -215,18 +215,19 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
+    const int seg_gx = std::max(SEG_GRID_X, std::min(592, N / 8192));     /* CTAs per segment: big single clouds need more */
     if (want_seg) {
         CK(cudaMemsetAsync(d.ccnt, 0, sizeof(int) * ((size_t)2 * nB << SP_HASH_BITS), st));
         mark(ctx, "memset_ccnt");
-        k_cl_count<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_count<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_count");
         k_cl_scan<<<2 * nB, 1024, 0, st>>>(d);
         mark(ctx, "k_cl_scan");
-        k_cl_scatter<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_scatter<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_scatter");
-        k_cl_union<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_union<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_union");
-        k_cl_flatten<<<dim3(SEG_GRID_X, 2 * nB), 256, 0, st>>>(d);
+        k_cl_flatten<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_flatten");
         k_cl_rank<<<2 * nB, RK_THREADS, 0, st>>>(d);
         mark(ctx, "k_cl_rank");
@@ -663,6 +664,40 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
         for (int i = 0; i < n; ++i) { xyz[3 * i] = a[idx[i]]; xyz[3 * i + 1] = b[idx[i]]; xyz[3 * i + 2] = c[idx[i]]; }
     }
     return n;
+}
+
+int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
+                   int32_t *max_pixel, int32_t *min_pixel)
+{
+    if (!ctx || !dir3 || frame < 0 || frame >= ctx->last_nB || plane < 0) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const SpDev &d = ctx->d;
+    const size_t N = ctx->N, f = frame;
+    sp_frame_result *r = new sp_frame_result;
+    cudaError_t e = cudaMemcpy(r, d.results + f, sizeof(*r), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || plane >= r->n_planes) { const bool bad = e == cudaSuccess; delete r; ctx->err = bad ? "plane out of range" : cudaGetErrorString(e); return bad ? SP_ERR_ARG : SP_ERR_CUDA; }
+    const sp_plane_record pr = r->planes[plane];
+    delete r;
+    const float *c = center3 ? center3 : pr.center;
+    k_minmax_proj<<<1, 256, 0, ctx->stream>>>(d, frame, pr.first, pr.count, c[0], c[1], c[2], dir3[0], dir3[1], dir3[2], ctx->d_order);
+    ctx->launches += 1;
+    int ord[2] = { -1, -1 };
+    CK(cudaMemcpyAsync(ord, ctx->d_order, sizeof(ord), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const float qnan = std::nanf("");
+    for (int w = 0; w < 2; ++w) {
+        float *xyz = w == 0 ? max_xyz : min_xyz; int32_t *pixel = w == 0 ? max_pixel : min_pixel;
+        int pix = -1;
+        if (ord[w] >= 0) CK(cudaMemcpy(&pix, d.plane_idx + f * N + pr.first + ord[w], 4, cudaMemcpyDeviceToHost));
+        if (pixel) *pixel = pix;
+        if (xyz) {
+            xyz[0] = xyz[1] = xyz[2] = qnan;
+            if (pix >= 0) { CK(cudaMemcpy(xyz, d.x + f * N + pix, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(xyz + 1, d.y + f * N + pix, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(xyz + 2, d.z + f * N + pix, 4, cudaMemcpyDeviceToHost)); }
+        }
+    }
+    return SP_OK;
 }
 
 } /* extern "C" */

@@ -928,3 +928,40 @@ __global__ void __launch_bounds__(256) k_gather_plane_points(SpDev d, const int 
         w += cnt; c = nxt[c];
     }
 }
+
+/* ==================================================================================================== */
+/* findMinMaxProjPoint, StairPerception.cpp:2780-2808: the two points of a plane whose projection of (p - centre) on a
+ * direction is largest / smallest (strict compares: the first such point wins).  One CTA over the plane's final point
+ * list; out = { ordinal of max, ordinal of min } (-1 when the plane is empty or no projection is comparable). */
+__global__ void __launch_bounds__(256) k_minmax_proj(SpDev d, int frame, int first, int n, float cx, float cy, float cz,
+                                                     float vx, float vy, float vz, int *out)
+{
+    __shared__ float smx[8], smn[8]; __shared__ int imx[8], imn[8];
+    const size_t base = (size_t)frame * d.N;
+    const int *idx = d.plane_idx + base + first;
+    float bmx = -FLT_MAX, bmn = FLT_MAX; int amx = -1, amn = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int pix = idx[i];
+        const float px = d.x[base + pix] - cx, py = d.y[base + pix] - cy, pz = d.z[base + pix] - cz;
+        const float proj = vx * px + (vy * py + vz * pz);            /* Eigen's unrolled 3-term reduction: c0 + (c1 + c2) */
+        if (proj > bmx) { bmx = proj; amx = i; }
+        if (proj < bmn) { bmn = proj; amn = i; }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_down_sync(0xffffffffu, bmx, o); const int i2 = __shfl_down_sync(0xffffffffu, amx, o);
+        if (i2 >= 0 && (amx < 0 || v2 > bmx || (v2 == bmx && i2 < amx))) { bmx = v2; amx = i2; }
+        const float w2 = __shfl_down_sync(0xffffffffu, bmn, o); const int j2 = __shfl_down_sync(0xffffffffu, amn, o);
+        if (j2 >= 0 && (amn < 0 || w2 < bmn || (w2 == bmn && j2 < amn))) { bmn = w2; amn = j2; }
+    }
+    if (lane == 0) { smx[wid] = bmx; imx[wid] = amx; smn[wid] = bmn; imn[wid] = amn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) {
+            if (imx[q] >= 0 && (amx < 0 || smx[q] > bmx || (smx[q] == bmx && imx[q] < amx))) { bmx = smx[q]; amx = imx[q]; }
+            if (imn[q] >= 0 && (amn < 0 || smn[q] < bmn || (smn[q] == bmn && imn[q] < amn))) { bmn = smn[q]; amn = imn[q]; }
+        }
+        out[0] = amx; out[1] = amn;
+    }
+}

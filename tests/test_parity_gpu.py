@@ -225,3 +225,20 @@ def test_knn_config4_two_million_points(sp, orc, synth):
     bad = compare_frame(ctx, 0, res, o, taps=["normals", "voxel_idx", "h_idx", "v_idx", "h_root", "v_root", "plane_idx"])
     assert not bad, "\n".join(bad[:20])
     ctx.close()
+
+
+def test_minmax_proj_on_device(sp, orc, samples, ctx1):
+    """a15 findMinMaxProjPoint (StairPerception.cpp:2780-2808) as an on-device reduction over a plane's point list"""
+    rec, w, h = samples["0001"]
+    res = ctx1.process_frames(rec)[0]
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(rec, w, h)
+    rng = np.random.default_rng(1)
+    for plane in range(int(res["n_planes"])):
+        for v in ([1, 0, 0], [0, 1, 0], [0, 0, -1], rng.normal(size=3)):
+            g = ctx1.minmax_proj(0, plane, v)
+            e = o.minmax_proj(plane, v)
+            assert same_bits(g[0], e[0]) and same_bits(g[1], e[1]) and g[2:] == e[2:], (plane, v)
+        g = ctx1.minmax_proj(0, plane, [0, 1, 0], center=[0.1, 0.2, 0.3])
+        e = o.minmax_proj(plane, [0, 1, 0], center=[0.1, 0.2, 0.3])
+        assert same_bits(g[0], e[0]) and g[2:] == e[2:]
