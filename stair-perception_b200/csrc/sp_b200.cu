@@ -244,7 +244,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     CK(cudaEventRecord(ctx->ev[4], st));
     if (all) {
         if (want_seg) {
-            k_merge<<<(nB + 31) / 32, 32, 0, st>>>(d, nB);
+            k_merge<<<(nB + MG_WARPS - 1) / MG_WARPS, MG_WARPS * 32, 0, st>>>(d, nB);
             mark(ctx, "k_merge");
             ctx->launches += 1;
             if (show_mode >= SP_SHOW_STAIR) {

@@ -593,9 +593,16 @@ __global__ void k_clear_planes(SpDev d, int nseg)
 }
 
 /* ==================================================================================================== */
-/* mergeSeperatedPlanes, StairPerception.cpp:965-1090: one thread per segment replays the sequential algorithm on
- * the (few) planes.  libc rand() is replaced by a per-frame restart of glibc's stream from seed 1 (the GUI's
- * srand(0) per redraw, modules/gui/gui.cpp:303, rewinds it the same way); horizontal planes draw first. */
+/* mergeSeperatedPlanes, StairPerception.cpp:965-1090: one warp per frame replays the sequential algorithm on the (few)
+ * planes; the lanes share the work inside a step (the 20 sample fetches of a plane, the 40 point-plane tests of a pair).
+ * libc rand() is replaced by a per-frame restart of glibc's stream from seed 1 (the GUI's srand(0) per redraw,
+ * modules/gui/gui.cpp:303, rewinds it the same way); horizontal planes draw first. */
+#define MG_WARPS 2
+struct MgWarp {
+    float sx[SP_PSEG][20], sy[SP_PSEG][20], sz[SP_PSEG][20];
+    int tail[SP_PSEG];
+};
+
 __device__ __forceinline__ int mg_point(const SpDev &d, int s, const SpSegPlane *chunks, const int *nxt, int head, int k)
 {
     int c = head;
@@ -604,64 +611,81 @@ __device__ __forceinline__ int mg_point(const SpDev &d, int s, const SpSegPlane 
     return d.plane_pts[(size_t)s * d.N + chunks[c].off + k];
 }
 
-__global__ void k_merge(SpDev d, int nB)
+__global__ void __launch_bounds__(MG_WARPS * 32) k_merge(SpDev d, int nB)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ MgWarp SW[MG_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.x * MG_WARPS + wid;
     if (f >= nB) return;
-    int rpos = 0;
+    MgWarp &S = SW[wid];
+    int rpos = 0;                                             /* warp-uniform position in the rand() stream */
     const float *X = d.x + (size_t)f * d.N, *Y = d.y + (size_t)f * d.N, *Z = d.z + (size_t)f * d.N;
     for (int hv = 0; hv < 2; ++hv) {
         const int s = 2 * f + hv;
         SpSegPlane *chunks = d.chunks + s * SP_PSEG;
         int *nxt = d.chunk_next + s * SP_PSEG;
         SpMergedPlane *mp = d.merged + s * SP_PSEG;
-        /* compact the plane slots (order = cluster rank, then call order) */
+        /* compact the plane slots into (cluster rank, call) order: rank sort, keys are unique */
         int P = min(d.n_seg[s], SP_PSEG);
-        for (int i = 0; i < P; ++i) {                         /* insertion sort by (cluster rank, call) */
+        for (int i = lane; i < P; i += 32) {
             const SpSegPlane pl = d.seg_planes[s * SP_PSEG + i];
-            int w = i;
-            while (w > 0 && (chunks[w - 1].cluster > pl.cluster || (chunks[w - 1].cluster == pl.cluster && chunks[w - 1].call > pl.call))) { chunks[w] = chunks[w - 1]; --w; }
-            chunks[w] = pl;
-        }
-        for (int i = 0; i < P; ++i) nxt[i] = -1;
-        d.n_seg[s] = P;
-        int tail[SP_PSEG];
-        for (int i = 0; i < P; ++i) {
-            mp[i].coef[0] = chunks[i].coef[0]; mp[i].coef[1] = chunks[i].coef[1]; mp[i].coef[2] = chunks[i].coef[2]; mp[i].coef[3] = chunks[i].coef[3];
-            mp[i].count = chunks[i].count; mp[i].head = i; tail[i] = i;
-        }
-        /* samples: 20 points per plane, index = rand() % (number of planes) */
-        float sx[SP_PSEG][20], sy[SP_PSEG][20], sz[SP_PSEG][20];
-        auto resample = [&](int i, int np) {
-            for (int j = 0; j < 20; ++j) {
-                const int r = d.rnd[(rpos++) & (SP_RAND_LEN - 1)];
-                const int pi = mg_point(d, s, chunks, nxt, mp[i].head, r % np);
-                sx[i][j] = X[pi]; sy[i][j] = Y[pi]; sz[i][j] = Z[pi];
+            int rank = 0;
+            for (int j = 0; j < P; ++j) {
+                const SpSegPlane &o = d.seg_planes[s * SP_PSEG + j];
+                rank += (o.cluster < pl.cluster || (o.cluster == pl.cluster && o.call < pl.call)) ? 1 : 0;
             }
+            chunks[rank] = pl;
+            nxt[rank] = -1;
+            S.tail[rank] = rank;
+            SpMergedPlane m0;
+            m0.coef[0] = pl.coef[0]; m0.coef[1] = pl.coef[1]; m0.coef[2] = pl.coef[2]; m0.coef[3] = pl.coef[3];
+            m0.count = pl.count; m0.head = rank; m0.pad0 = m0.pad1 = 0;
+            mp[rank] = m0;
+        }
+        if (lane == 0) d.n_seg[s] = P;
+        __syncwarp();
+        /* samples: 20 points per plane, index = rand() % (number of planes) */
+        auto resample = [&](int i, int np) {
+            if (lane < 20) {
+                const int r = d.rnd[(rpos + lane) & (SP_RAND_LEN - 1)];
+                const int pi = mg_point(d, s, chunks, nxt, mp[i].head, r % np);
+                S.sx[i][lane] = X[pi]; S.sy[i][lane] = Y[pi]; S.sz[i][lane] = Z[pi];
+            }
+            rpos += 20;
+            __syncwarp();
         };
         for (int i = 0; i < P; ++i) resample(i, P);
         for (int i = 0; i < P; ++i) {
-            const float a1 = mp[i].coef[0], b1 = mp[i].coef[1], c1 = mp[i].coef[2], d1 = mp[i].coef[3];
-            float s1x[20], s1y[20], s1z[20];
-            for (int k = 0; k < 20; ++k) { s1x[k] = sx[i][k]; s1y[k] = sy[i][k]; s1z[k] = sz[i][k]; }
             for (int j = i + 1; j < P; ++j) {
+                const float a1 = mp[i].coef[0], b1 = mp[i].coef[1], c1 = mp[i].coef[2], d1 = mp[i].coef[3];
                 const float a2 = mp[j].coef[0], b2 = mp[j].coef[1], c2 = mp[j].coef[2], d2 = mp[j].coef[3];
                 const float dot = a1 * a2 + (b1 * b2 + c1 * c2);
                 const float angle = det_acosf(dot);
                 if (((double)angle < d.c.merge_ath) || (3.14159265358979323846 - (double)angle < d.c.merge_ath)) {
-                    int count = 0;
-                    for (int k = 0; k < 20; ++k) { const float dd = fabsf(a2 * s1x[k] + b2 * s1y[k] + c2 * s1z[k] + d2); if (dd <= d.c.merge_thr) count++; }
-                    for (int k = 0; k < 20; ++k) { const float dd = fabsf(a1 * sx[j][k] + b1 * sy[j][k] + c1 * sz[j][k] + d1); if (dd <= d.c.merge_thr) count++; }
+                    bool near = false;
+                    if (lane < 20) near = fabsf(a2 * S.sx[i][lane] + b2 * S.sy[i][lane] + c2 * S.sz[i][lane] + d2) <= d.c.merge_thr;
+                    int count = __popc(__ballot_sync(0xffffffffu, near));
+                    near = false;
+                    if (lane < 20) near = fabsf(a1 * S.sx[j][lane] + b1 * S.sy[j][lane] + c1 * S.sz[j][lane] + d1) <= d.c.merge_thr;
+                    count += __popc(__ballot_sync(0xffffffffu, near));
                     if (count > 20) {
                         const int n1 = mp[i].count, n2 = mp[j].count, nn = n1 + n2;
                         float a, b, c, dd;
                         if (dot > 0) { a = (a1 * n1 + a2 * n2) / nn; b = (b1 * n1 + b2 * n2) / nn; c = (c1 * n1 + c2 * n2) / nn; dd = (d1 * n1 + d2 * n2) / nn; }
                         else { a = (a1 * n1 - a2 * n2) / nn; b = (b1 * n1 - b2 * n2) / nn; c = (c1 * n1 - c2 * n2) / nn; dd = (d1 * n1 - d2 * n2) / nn; }
-                        nxt[tail[i]] = mp[j].head; tail[i] = tail[j];
-                        mp[i].coef[0] = a; mp[i].coef[1] = b; mp[i].coef[2] = c; mp[i].coef[3] = dd; mp[i].count = nn;
+                        __syncwarp();
+                        if (lane == 0) {
+                            nxt[S.tail[i]] = mp[j].head; S.tail[i] = S.tail[j];
+                            mp[i].coef[0] = a; mp[i].coef[1] = b; mp[i].coef[2] = c; mp[i].coef[3] = dd; mp[i].count = nn;
+                            for (int t = j; t + 1 < P; ++t) { mp[t] = mp[t + 1]; S.tail[t] = S.tail[t + 1]; }
+                        }
+                        __syncwarp();
                         for (int t = j; t + 1 < P; ++t) {
-                            mp[t] = mp[t + 1]; tail[t] = tail[t + 1];
-                            for (int k = 0; k < 20; ++k) { sx[t][k] = sx[t + 1][k]; sy[t][k] = sy[t + 1][k]; sz[t][k] = sz[t + 1][k]; }
+                            float vx = 0.f, vy = 0.f, vz = 0.f;
+                            if (lane < 20) { vx = S.sx[t + 1][lane]; vy = S.sy[t + 1][lane]; vz = S.sz[t + 1][lane]; }
+                            __syncwarp();
+                            if (lane < 20) { S.sx[t][lane] = vx; S.sy[t][lane] = vy; S.sz[t][lane] = vz; }
+                            __syncwarp();
                         }
                         --P;
                         resample(i, P);
@@ -670,7 +694,8 @@ __global__ void k_merge(SpDev d, int nB)
                 }
             }
         }
-        d.n_merged[s] = P;
+        if (lane == 0) d.n_merged[s] = P;
+        __syncwarp();
     }
 }
 
