@@ -16,7 +16,6 @@
 #define SP_DETMATH_H_
 
 #include <math.h>
-#include <string.h>
 #include <float.h>
 
 #ifdef __CUDACC__
@@ -274,36 +273,6 @@ SP_HD void det_jacobi3f(const float *cov /* row-major */, float *evals, float *e
         evals[j] = d[ord[j]];
         for (int k = 0; k < 3; ++k) evecs[k * 3 + j] = v[k][ord[j]];
     }
-}
-
-/* ---- exact fixed-point image of a float: round-to-nearest-even of clamp(g, +-8192) * 2^44 as int64 ---------- */
-/* The organised-normal box sums (pcl::IntegralImageNormalEstimation accumulates the float gradients in double) are
- * defined here as EXACT integer sums of these values, so any summation order -- and therefore any parallel
- * decomposition -- gives the same bits.  2^-44 m is below the rounding noise of PCL's own double integral images;
- * 25 * 8192 * 2^44 < 2^62 cannot overflow.  g must be finite.  Integer-only: no float->double->int64 conversions. */
-SP_HD long long det_fix44(float g)
-{
-    g = g < -8192.0f ? -8192.0f : (g > 8192.0f ? 8192.0f : g);
-    unsigned u;
-#ifdef __CUDA_ARCH__
-    u = __float_as_uint(g);
-#else
-    memcpy(&u, &g, 4);
-#endif
-    const int e = (int)((u >> 23) & 255u);
-    const unsigned m = (u & 0x7fffffu) | 0x800000u;
-    const int sh = e - 106;                                   /* value = m * 2^(e - 150); times 2^44 */
-    unsigned long long q;
-    if (sh >= 0) q = (unsigned long long)m << sh;             /* sh <= 34 after the clamp */
-    else {
-        const int r = -sh;
-        if (r > 25) q = 0;                                    /* below a quarter unit (also zero and denormals) */
-        else {
-            const unsigned fl = m >> r, rem = m & ((1u << r) - 1u), half = 1u << (r - 1);
-            q = fl + ((rem > half || (rem == half && (fl & 1u))) ? 1u : 0u);
-        }
-    }
-    return (u >> 31) ? -(long long)q : (long long)q;
 }
 
 #endif /* SP_DETMATH_H_ */

@@ -79,7 +79,6 @@ def lib():
         L.orc_mt19937_draws.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         L.orc_minmax_proj.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_fix44.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_eigen33.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_jacobi3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L

@@ -47,7 +47,7 @@ const char *kStageNames[ST_COUNT] = { "level_mask", "normals", "crop", "voxel", 
 
 struct orc_ctx {
     orc_params p;
-    int normal_arith = 1;    /* 0 = PCL integral images (double), 1 = exact fixed-point box sums (the portable definition) */
+    int normal_arith = 1;    /* 0 = PCL integral images (double), 1 = fixed-order double box sums */
     int voxel_order = 0;     /* 0 = stable, 1 = std::sort on the key only */
     int eig_math = 0;        /* 0 = portable det_* math, 1 = libm */
     int knn_threads = 8;     /* host threads of the kNN normal search (a3') */
@@ -108,13 +108,6 @@ void level_and_mask(orc_ctx *c, const uint8_t *rec, const float *R)
 /* a3: pcl::IntegralImageNormalEstimation, AVERAGE_3D_GRADIENT, MaxDepthChangeFactor 0.02, NormalSmoothingSize 5,
  * BORDER_POLICY_IGNORE, no depth-dependent smoothing (StairPerception.cpp:579-592; upstream
  * features/impl/integral_image_normal.hpp, features/impl/integral_image2D.hpp).                          */
-/* independent statement of the fixed-point image (the product's integer-only det_fix44 is checked against it) */
-static inline int64_t fix44_ref(float g)
-{
-    const float cl = g < -8192.0f ? -8192.0f : (g > 8192.0f ? 8192.0f : g);
-    return (int64_t)llrint((double)cl * 17592186044416.0);
-}
-
 void normals_integral(orc_ctx *c)
 {
     const int W = c->W, H = c->H, N = c->N;
@@ -205,19 +198,19 @@ void normals_integral(orc_ctx *c)
                     sgy[q] = IY[3 * lr + q] + IY[3 * ul + q] - IY[3 * ur + q] - IY[3 * ll + q];
                 }
             } else {
-                /* portable definition the CUDA kernels reproduce: EXACT box sums.  Every finite gradient element goes to
-                 * fixed point, q = llrint(clamp(g, +-8192) * 2^44), and the window sum is an integer sum -- independent of
-                 * summation order, hence of any parallel decomposition.  (PCL accumulates the same floats in double
-                 * integral images; 2^-44 m is below that scheme's own rounding noise.) */
-                int64_t ax[3] = { 0, 0, 0 }, ay[3] = { 0, 0, 0 };
-                for (int rr = 0; rr < k; ++rr)
+                /* fixed-order definition the CUDA kernel reproduces: S = sum over rows (top to bottom) of the
+                 * row sums (left to right), all in double, non-finite elements contributing +0.0 */
+                for (int q = 0; q < 3; ++q) sgx[q] = sgy[q] = 0.0;
+                for (int rr = 0; rr < k; ++rr) {
+                    double rx[3] = { 0, 0, 0 }, ry[3] = { 0, 0, 0 };
                     for (int cc = 0; cc < k; ++cc) {
                         const size_t j = (size_t)(sy + rr) * W + (sx + cc);
                         const float *ex = &gx[3 * j], *ey = &gy[3 * j];
-                        if (elem_finite(ex)) { ++cntx; for (int q = 0; q < 3; ++q) ax[q] += fix44_ref(ex[q]); }
-                        if (elem_finite(ey)) { ++cnty; for (int q = 0; q < 3; ++q) ay[q] += fix44_ref(ey[q]); }
+                        if (elem_finite(ex)) { ++cntx; for (int q = 0; q < 3; ++q) rx[q] += (double)ex[q]; }
+                        if (elem_finite(ey)) { ++cnty; for (int q = 0; q < 3; ++q) ry[q] += (double)ey[q]; }
                     }
-                for (int q = 0; q < 3; ++q) { sgx[q] = (double)ax[q]; sgy[q] = (double)ay[q]; }
+                    for (int q = 0; q < 3; ++q) { sgx[q] += rx[q]; sgy[q] += ry[q]; }
+                }
             }
             if (cntx == 0 || cnty == 0) continue;
             double n0 = sgy[1] * sgx[2] - sgy[2] * sgx[1];
@@ -225,14 +218,8 @@ void normals_integral(orc_ctx *c)
             double n2 = sgy[0] * sgx[1] - sgy[1] * sgx[0];
             const double L = n0 * n0 + (n1 * n1 + n2 * n2);
             if (L == 0.0) continue;
-            float fx, fy, fz;
-            if (c->normal_arith == 0) {                                     /* Eigen >= 3.3: vector /= scalar divides */
-                const double sq = sqrt(L);
-                fx = (float)(n0 / sq); fy = (float)(n1 / sq); fz = (float)(n2 / sq);
-            } else {                                                        /* Eigen 3.2: vector /= scalar multiplies by 1/scalar */
-                const double inv = 1.0 / sqrt(L);
-                fx = (float)(n0 * inv); fy = (float)(n1 * inv); fz = (float)(n2 * inv);
-            }
+            const double sq = sqrt(L);
+            float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
             /* pcl::flipNormalTowardsViewpoint, viewpoint = sensor origin 0 (features/normal_3d.h) */
             const float vx = 0.0f - X[i], vy = 0.0f - Y[i], vz = 0.0f - Z[i];
             const float cs = (vx * fx + vy * fy + vz * fz);
@@ -999,9 +986,6 @@ void orc_mt19937_draws(uint32_t seed, int n, int32_t *out) { std::mt19937 r(seed
 void orc_glibc_rand(uint32_t seed, int n, int32_t *out) { glibc_rand_stream(seed, n, out); }
 void orc_eigen33(const float *cov9, int libm, float *ev, float *evec) { if (libm) det_eigen33f<1>(cov9, ev, evec); else det_eigen33f<0>(cov9, ev, evec); }
 void orc_jacobi3(const float *cov9, float *evals3, float *evecs9) { det_jacobi3f(cov9, evals3, evecs9); }
-
-/* fixed-point image of floats: which = 0 the oracle's llrint statement, 1 = the product header's integer-only det_fix44 */
-void orc_fix44(const float *g, int n, int which, int64_t *out) { for (int i = 0; i < n; ++i) out[i] = which ? (int64_t)det_fix44(g[i]) : fix44_ref(g[i]); }
 
 /* findMinMaxProjPoint, StairPerception.cpp:2780-2808, on plane `plane` of the last frame processed */
 int orc_minmax_proj(orc_ctx *c, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz, int32_t *max_pixel, int32_t *min_pixel)

@@ -65,8 +65,8 @@ void orc_destroy(orc_ctx *c);
 
 /* Arithmetic modes.  name/value:
  *   "normal_arith": 0 = PCL integral images with double accumulators (faithful restatement),
- *                   1 = exact box sums: gradients to fixed point (2^-44 m), integer window sums, normalisation by
- *                       multiplying with 1/sqrt (the portable definition the CUDA kernels reproduce bit for bit).  Default 1.
+ *                   1 = "box32": direct k x k box sums in float32 in the fixed order documented in DESIGN.md
+ *                       (the portable definition the CUDA kernel reproduces bit for bit).  Default 1.
  *   "voxel_order":  0 = stable (ascending input index inside a voxel; the documented rule), default;
  *                   1 = libstdc++ std::sort on the key only (what the reference binary would do with g++).
  *   "eig_math":     0 = portable det_* trig from include/sp_detmath.h (default), 1 = libm.
@@ -110,9 +110,6 @@ void orc_glibc_rand(uint32_t seed, int n, int32_t *out);      /* glibc TYPE_3 ra
 void orc_eigen33(const float *cov9, int libm, float *eigenvalue, float *eigenvector3);
 /* symmetric 3x3 Jacobi eigen decomposition (descending), vectors as columns, row-major 9 */
 void orc_jacobi3(const float *cov9, float *evals3, float *evecs9);
-
-/* fixed-point image used by the exact box sums; which: 0 = oracle statement (llrint), 1 = include/sp_detmath.h det_fix44 */
-void orc_fix44(const float *g, int n, int which, int64_t *out);
 
 /* findMinMaxProjPoint (StairPerception.cpp:2780-2808) on plane `plane` of the last processed frame; center3 NULL = plane centre */
 int orc_minmax_proj(orc_ctx *c, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,

@@ -183,27 +183,27 @@ __global__ void __launch_bounds__(K1_THREADS) k_ingest_normals(SpDev d)
             if (k >= 2) {
                 const int half = k >> 1;
                 const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
-                /* exact box sums: fixed-point images of the gradient elements (include/sp_detmath.h), integer adds */
-                long long ax0 = 0, ax1 = 0, ax2 = 0, ay0 = 0, ay1 = 0, ay2 = 0;
+                double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
                 int cntx = 0, cnty = 0;
                 for (int a = 0; a < k; ++a) {
+                    double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
                     const int gb = g0 + a * K1_GW;
                     for (int b = 0; b < k; ++b) {
                         const int ge = gb + b;
-                        ax0 += det_fix44(s.gx[0][ge]); ax1 += det_fix44(s.gx[1][ge]); ax2 += det_fix44(s.gx[2][ge]);
-                        ay0 += det_fix44(s.gy[0][ge]); ay1 += det_fix44(s.gy[1][ge]); ay2 += det_fix44(s.gy[2][ge]);
+                        rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
+                        ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
                         cntx += s.fx[ge]; cnty += s.fy[ge];
                     }
+                    sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
                 }
-                const double sgx0 = (double)ax0, sgx1 = (double)ax1, sgx2 = (double)ax2, sgy0 = (double)ay0, sgy1 = (double)ay1, sgy2 = (double)ay2;
                 if (cntx != 0 && cnty != 0) {
                     const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
                     const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
                     const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
                     const double L = n0 * n0 + (n1 * n1 + n2 * n2);
                     if (L != 0.0) {
-                        const double inv = 1.0 / sqrt(L);
-                        float fx = (float)(n0 * inv), fy = (float)(n1 * inv), fz = (float)(n2 * inv);
+                        const double sq = sqrt(L);
+                        float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
                         const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
                         const float cs = (vx * fx + vy * fy + vz * fz);
                         if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
