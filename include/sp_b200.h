@@ -126,6 +126,20 @@ int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nfr
 int sp_process_frames_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int show_mode,
                              sp_frame_result *results);
 
+/* Depth-image ingest -- the step BEFORE the path, so that 2-8 bytes per pixel cross PCIe instead of 16:
+ * replaces K2G::updateCloud (/root/reference/modules/k2g/k2g.cpp:231-308, pinhole maps of K2G::prepareMake3D :506-520)
+ * followed by everything sp_process_frames does.
+ *   depth      : nframes x width*height undistorted depth in millimetres; depth_type 0 = float32 (libfreenect2's undistorted
+ *                frame), 1 = uint16 (the depth PNG of Reader::save_images, test/reader.cpp:128)
+ *   bgrx       : registered colour, 4 bytes per pixel (b, g, r, unused), or NULL = every valid pixel white.  The front-end's
+ *                validity mask is "r, g and b all non-zero" (StairPerception.cpp:338-356), so colour matters.
+ *   K          : IR camera intrinsics (libfreenect2 IrCameraParams fx, fy, cx, cy)
+ *   mirror     : the horizontal flip of K2G(true) (k2g.cpp:247-253)
+ * The frame loaded after the call (taps, sp_copy_plane_points) is indexed like the cloud: pixel = row * width + column. */
+typedef struct sp_intrinsics { float fx, fy, cx, cy; } sp_intrinsics;
+int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, const uint8_t *bgrx, const sp_intrinsics *K, int mirror,
+                            const float *R9, int nframes, int show_mode, sp_frame_result *results);
+
 /* Stage taps of the LAST chunk processed (the ShowModeDef taps of process(), StairPerception.cpp:49-176, plus
  * the intermediate arrays the parity tests compare).  `frame` indexes the last chunk.  Names:
  *   "xyz" (N x 3 float, levelled+masked)  "normals" (N x 3 float)  "minmax" (6 float)  "voxel_key" (N u32)

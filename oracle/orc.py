@@ -78,6 +78,7 @@ def lib():
         L.orc_rotation_from_quat.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_mt19937_draws.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_depth_to_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]
         L.orc_minmax_proj.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_eigen33.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_jacobi3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -195,3 +196,17 @@ def glibc_rand(seed, n):
     out = np.zeros(n, dtype=np.int32)
     lib().orc_glibc_rand(seed, n, out.ctypes.data)
     return out
+
+
+def depth_to_cloud(depth, intrinsics, bgrx=None, mirror=True):
+    """K2G::updateCloud on the CPU: depth (H, W) float32 or uint16 millimetres -> records[H*W] {x,y,z,rgba}"""
+    depth = np.ascontiguousarray(depth)
+    H, W = depth.shape
+    rec = np.zeros(W * H, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    cp = None
+    if bgrx is not None:
+        bgrx = np.ascontiguousarray(bgrx, dtype=np.uint8)
+        cp = bgrx.ctypes.data
+    lib().orc_depth_to_cloud(depth.ctypes.data, 0 if depth.dtype == np.float32 else 1, cp, W, H, fx, fy, cx, cy, 1 if mirror else 0, rec.ctypes.data)
+    return rec

@@ -987,6 +987,34 @@ void orc_glibc_rand(uint32_t seed, int n, int32_t *out) { glibc_rand_stream(seed
 void orc_eigen33(const float *cov9, int libm, float *ev, float *evec) { if (libm) det_eigen33f<1>(cov9, ev, evec); else det_eigen33f<0>(cov9, ev, evec); }
 void orc_jacobi3(const float *cov9, float *evals3, float *evecs9) { det_jacobi3f(cov9, evals3, evecs9); }
 
+/* K2G::updateCloud + K2G::prepareMake3D, /root/reference/modules/k2g/k2g.cpp:231-308, :506-520: undistorted depth (mm) and
+ * registered colour -> the XYZRGBA cloud (16-byte records).  depth_type 0 = float32, 1 = uint16. */
+void orc_depth_to_cloud(const void *depth, int depth_type, const uint8_t *bgrx, int W, int H, float fx, float fy, float cx, float cy,
+                        int mirror, void *out_records)
+{
+    std::vector<float> colmap(W), rowmap(H);
+    for (int i = 0; i < W; i++) colmap[i] = (float)((i - cx + 0.5) / fx);
+    for (int i = 0; i < H; i++) rowmap[i] = (float)((i - cy + 0.5) / fy);
+    uint8_t *out = (uint8_t *)out_records;
+    for (int y = 0; y < H; ++y) {
+        const float dy = rowmap[y];
+        for (int x = 0; x < W; ++x) {
+            const int sx = mirror ? (W - 1 - x) : x;                       /* cv::flip(.., 1) before the loop */
+            const size_t si = (size_t)y * W + sx;
+            const float raw = depth_type == 0 ? ((const float *)depth)[si] : (float)((const uint16_t *)depth)[si];
+            const float depth_value = raw / 1000.0f;
+            float px, py, pz; uint32_t rgba;
+            if (!std::isnan(depth_value) && !(std::abs(depth_value) < 0.0001)) {
+                px = colmap[x] * depth_value; py = dy * depth_value; pz = depth_value;
+                rgba = 0xFFFFFFFFu;
+                if (bgrx) rgba = (uint32_t)bgrx[4 * si] | ((uint32_t)bgrx[4 * si + 1] << 8) | ((uint32_t)bgrx[4 * si + 2] << 16) | 0xFF000000u;
+            } else { px = py = pz = kNaN; rgba = 0; }
+            uint8_t *o = out + 16 * ((size_t)y * W + x);
+            memcpy(o, &px, 4); memcpy(o + 4, &py, 4); memcpy(o + 8, &pz, 4); memcpy(o + 12, &rgba, 4);
+        }
+    }
+}
+
 /* findMinMaxProjPoint, StairPerception.cpp:2780-2808, on plane `plane` of the last frame processed */
 int orc_minmax_proj(orc_ctx *c, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz, int32_t *max_pixel, int32_t *min_pixel)
 {

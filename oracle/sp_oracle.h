@@ -111,6 +111,10 @@ void orc_eigen33(const float *cov9, int libm, float *eigenvalue, float *eigenvec
 /* symmetric 3x3 Jacobi eigen decomposition (descending), vectors as columns, row-major 9 */
 void orc_jacobi3(const float *cov9, float *evals3, float *evecs9);
 
+/* K2G::updateCloud (k2g.cpp:231-308): depth image (mm; type 0 float32, 1 uint16) + registered colour (b,g,r,x or NULL) -> records */
+void orc_depth_to_cloud(const void *depth, int depth_type, const uint8_t *bgrx, int W, int H, float fx, float fy, float cx, float cy,
+                        int mirror, void *out_records);
+
 /* findMinMaxProjPoint (StairPerception.cpp:2780-2808) on plane `plane` of the last processed frame; center3 NULL = plane centre */
 int orc_minmax_proj(orc_ctx *c, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
                     int32_t *max_pixel, int32_t *min_pixel);

@@ -67,6 +67,7 @@ def lib():
         L.sp_launch_count.restype = C.c_int64
         L.sp_launch_count.argtypes = [C.c_void_p]
         L.sp_run_stage_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sp_process_depth_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.sp_minmax_proj.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sp_set_normal_mode.argtypes = [C.c_void_p, C.c_int]
         L.sp_set_trace.argtypes = [C.c_void_p, C.c_int]
@@ -161,6 +162,23 @@ class Context:
             Rp = _ptr(R)
         fn = self.L.sp_process_frames_device if device_input else self.L.sp_process_frames
         self._check(fn(self.h, _ptr(clouds), Rp, nframes, int(show_mode), results.ctypes.data), "sp_process_frames")
+        return results
+
+    def process_depth_frames(self, depth, intrinsics, bgrx=None, mirror=True, R=None, show_mode=10, nframes=None, results=None):
+        """depth: float32 or uint16 millimetres, nframes x H x W (numpy or pinned torch CPU tensor); intrinsics = (fx, fy, cx, cy);
+        bgrx: optional registered colour, nframes x H x W x 4 uint8.  Returns FRAME_DTYPE records."""
+        itemsize = depth.dtype.itemsize if isinstance(depth, np.ndarray) else depth.element_size()
+        if itemsize not in (2, 4):
+            raise ValueError("depth must be float32 or uint16")
+        nbytes = depth.nbytes if isinstance(depth, np.ndarray) else depth.numel() * itemsize
+        if nframes is None:
+            nframes = nbytes // (self.N * itemsize)
+        if results is None:
+            results = np.zeros(nframes, dtype=FRAME_DTYPE)
+        K = (C.c_float * 4)(*[float(v) for v in intrinsics])
+        self._check(self.L.sp_process_depth_frames(self.h, _ptr(depth), 0 if itemsize == 4 else 1, None if bgrx is None else _ptr(bgrx), K,
+                                                   1 if mirror else 0, None if R is None else _ptr(R), nframes, int(show_mode), results.ctypes.data),
+                    "sp_process_depth_frames")
         return results
 
     def run_stage_device(self, clouds_ptr, R_ptr, nframes, stage):

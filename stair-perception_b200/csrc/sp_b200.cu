@@ -117,6 +117,9 @@ struct sp_ctx {
     int *knn_mm = nullptr, *knn_bstart = nullptr, *knn_bend = nullptr;
     SpKnnGrid *knn_grid = nullptr;
     float4 *knn_pts = nullptr;
+    /* depth-image ingest (sp_process_depth_frames): staging buffers, allocated on first use */
+    void *d_depth[2] = { nullptr, nullptr }; unsigned char *d_color[2] = { nullptr, nullptr };
+    float *d_maps = nullptr;                 /* colmap[W] then rowmap[H] */
     bool trace = false;
     std::vector<cudaEvent_t> tev;
     std::vector<const char *> tname;
@@ -443,6 +446,66 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         }
         CK(cudaMemsetAsync(ctx->d.results, 0, sizeof(sp_frame_result) * nB, ctx->stream));
         const int rc = run_chunk(ctx, din, dR, nB, show_mode, -1);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_results, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(results + f0, ctx->h_results, sizeof(sp_frame_result) * nB);
+        buf ^= 1;
+    }
+    collect_times(ctx);
+    return SP_OK;
+}
+
+int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, const uint8_t *bgrx, const sp_intrinsics *K, int mirror,
+                            const float *R9, int nframes, int show_mode, sp_frame_result *results)
+{
+    if (!ctx || !depth || !K || (depth_type != 0 && depth_type != 1) || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR ||
+        (!results && nframes > 0) || !(K->fx != 0.f) || !(K->fy != 0.f)) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (show_mode == SP_SHOW_ORIGINAL) { memset(results, 0, sizeof(sp_frame_result) * (size_t)nframes); return SP_OK; }
+    const size_t N = ctx->N, B = ctx->B, dsz = depth_type == 0 ? 4 : 2;
+    if (!ctx->d_maps) {
+        cudaError_t e;
+        for (int i = 0; i < 2; ++i) {
+            void *q = nullptr;
+            if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ctx->err = std::string("cudaMalloc (depth staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+            ctx->allocs.push_back(q); ctx->d_depth[i] = q;
+            if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ctx->err = std::string("cudaMalloc (colour staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+            ctx->allocs.push_back(q); ctx->d_color[i] = (unsigned char *)q;
+        }
+        if ((e = dalloc(ctx, &ctx->d_maps, (size_t)ctx->W + ctx->H)) != cudaSuccess) { ctx->err = std::string("cudaMalloc (maps): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+    }
+    {
+        /* K2G::prepareMake3D, k2g.cpp:506-520: (i - c + 0.5) / f evaluated in double, stored as float */
+        std::vector<float> maps((size_t)ctx->W + ctx->H);
+        for (int i = 0; i < ctx->W; ++i) maps[i] = (float)((i - K->cx + 0.5) / K->fx);
+        for (int i = 0; i < ctx->H; ++i) maps[(size_t)ctx->W + i] = (float)((i - K->cy + 0.5) / K->fy);
+        CK(cudaMemcpyAsync(ctx->d_maps, maps.data(), maps.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const int nchunks = (nframes + ctx->B - 1) / ctx->B;
+    auto issue_copy = [&](int ci, int b) -> int {
+        const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CK(cudaMemcpyAsync(ctx->d_depth[b], (const uint8_t *)depth + N * dsz * f0, N * dsz * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (bgrx) CK(cudaMemcpyAsync(ctx->d_color[b], bgrx + N * 4 * f0, N * 4 * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (R9) CK(cudaMemcpyAsync(ctx->d_R[b], R9 + 9 * (size_t)f0, sizeof(float) * 9 * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+        return SP_OK;
+    };
+    int buf = 0;
+    if (nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
+        if (ci + 1 < nchunks) { const int rc = issue_copy(ci + 1, buf ^ 1); if (rc) return rc; }
+        k_depth_to_records<<<dim3(std::min(ctx->d.nblk, 148), nB), 256, 0, ctx->stream>>>(ctx->d_depth[buf], depth_type, bgrx ? ctx->d_color[buf] : nullptr,
+                                                                                             ctx->d_maps, ctx->d_maps + ctx->W, ctx->W, ctx->H, mirror ? 1 : 0, ctx->d_in[buf]);
+        ctx->launches += 1;
+        CK(cudaMemsetAsync(ctx->d.results, 0, sizeof(sp_frame_result) * nB, ctx->stream));
+        const int rc = run_chunk(ctx, ctx->d_in[buf], R9 ? ctx->d_R[buf] : nullptr, nB, show_mode, -1);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_results, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));

@@ -389,3 +389,35 @@ __global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
         b_v += tot;
     }
 }
+
+/* ==================================================================================================== */
+/* Depth-image ingest: K2G::updateCloud (/root/reference/modules/k2g/k2g.cpp:231-308) with the pinhole maps of
+ * K2G::prepareMake3D (:506-520), on the device: (undistorted depth in mm, registered colour) -> the 16-byte cloud records
+ * the front-end reads.  depth_type 0 = float32 mm (libfreenect2's undistorted frame), 1 = uint16 mm (the saved depth PNG,
+ * test/reader.cpp:128).  bgrx = registered colour, 4 bytes per pixel (b, g, r, x) or NULL (every valid pixel white).
+ * mirror = the horizontal flip of K2G(true) (k2g.cpp:247-253, test/reader.cpp:9). */
+__global__ void __launch_bounds__(256) k_depth_to_records(const void *depth, int depth_type, const unsigned char *bgrx, const float *colmap,
+                                                          const float *rowmap, int W, int H, int mirror, float4 *out)
+{
+    const int f = blockIdx.y, N = W * H;
+    const size_t base = (size_t)f * N;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        const int sx = mirror ? (W - 1 - x) : x;
+        const size_t si = base + (size_t)y * W + sx;
+        const float dmm = depth_type == 0 ? reinterpret_cast<const float *>(depth)[si] : (float)reinterpret_cast<const unsigned short *>(depth)[si];
+        const float dv = dmm / 1000.0f;
+        float4 o;
+        if (!isnan(dv) && !(fabsf(dv) < 0.0001)) {
+            o.x = colmap[x] * dv; o.y = rowmap[y] * dv; o.z = dv;
+            unsigned rgba = 0xFFFFFFFFu;
+            if (bgrx) { const uchar4 c = reinterpret_cast<const uchar4 *>(bgrx)[si]; rgba = (unsigned)c.x | ((unsigned)c.y << 8) | ((unsigned)c.z << 16) | 0xFF000000u; }
+            o.w = __uint_as_float(rgba);
+        } else {
+            o.x = o.y = o.z = qnan;
+            o.w = __uint_as_float(0u);                /* b = g = r = (uint8)NaN: 0 on x86, and alpha is left unset */
+        }
+        out[base + i] = o;
+    }
+}

@@ -97,6 +97,22 @@ def make_frame(frame_id=0, rise=0.11, run=0.28, width=1.0, n_steps=4, jitter=Tru
     return rec, R.astype(np.float32).reshape(9)
 
 
+INTRINSICS = (FX, FY, CX, CY)
+
+
+def make_depth_frame(frame_id=0, **kw):
+    """The same scene as make_frame(frame_id), as what the sensor side delivers before K2G::updateCloud: a 424 x 512 uint16
+    depth image in millimetres (0 = no return; un-mirrored, i.e. before the horizontal flip of K2G(true)), a registered colour
+    image (b, g, r, x; the front-end's validity mask needs non-zero channels) and the levelling rotation."""
+    rec, R = make_frame(frame_id, **kw)
+    valid = ((rec["rgba"] & 255) != 0) & (((rec["rgba"] >> 8) & 255) != 0) & (((rec["rgba"] >> 16) & 255) != 0)
+    depth = np.where(valid, np.round(rec["z"].astype(np.float64) * 1000.0), 0).astype(np.uint16).reshape(H, W)[:, ::-1].copy()
+    bgrx = np.zeros((H, W, 4), dtype=np.uint8)
+    rgba = rec["rgba"].reshape(H, W)[:, ::-1]
+    bgrx[..., 0], bgrx[..., 1], bgrx[..., 2] = rgba & 255, (rgba >> 8) & 255, (rgba >> 16) & 255
+    return depth, bgrx, R
+
+
 def make_batch(n, first_id=0, **kw):
     recs, Rs = [], []
     for i in range(n):

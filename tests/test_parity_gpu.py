@@ -242,3 +242,31 @@ def test_minmax_proj_on_device(sp, orc, samples, ctx1):
         g = ctx1.minmax_proj(0, plane, [0, 1, 0], center=[0.1, 0.2, 0.3])
         e = o.minmax_proj(plane, [0, 1, 0], center=[0.1, 0.2, 0.3])
         assert same_bits(g[0], e[0]) and g[2:] == e[2:]
+
+
+@pytest.mark.parametrize("dtype,with_colour", [(np.uint16, True), (np.float32, True), (np.uint16, False)])
+def test_depth_image_ingest(sp, orc, synth, dtype, with_colour):
+    """next-row f2: K2G::updateCloud (k2g.cpp:231-308) on the device in front of the path.  The records the kernel builds from
+    (depth, colour, intrinsics, mirror) equal the oracle's back-projection bit for bit, and so does everything downstream."""
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=2)
+    frames = [synth.make_depth_frame(fid) for fid in (21, 22, 23)]
+    depth = np.stack([f[0] for f in frames]).astype(dtype)
+    if dtype == np.float32:
+        depth[0, 5, 7] = np.nan                         # libfreenect2 marks some invalid pixels NaN instead of 0
+    bgrx = np.stack([f[1] for f in frames]) if with_colour else None
+    R = np.stack([f[2] for f in frames])
+    res = ctx.process_depth_frames(depth, synth.INTRINSICS, bgrx=bgrx, mirror=True, R=R)
+    assert len(res) == 3
+    i = 2                                               # the last chunk (frames 2) still sits in the context
+    rec = orc.depth_to_cloud(depth[i], synth.INTRINSICS, None if bgrx is None else bgrx[i], mirror=True)
+    o = orc.Oracle(sp.DEFAULT_PARAMS)
+    o.process(rec, 512, 424, R[i])
+    bad = compare_frame(ctx, 0, res[i], o)
+    assert not bad, "\n".join(bad[:20])
+    assert int(res[i]["n_planes"]) >= 8
+    for j in (0, 1):
+        rec = orc.depth_to_cloud(depth[j], synth.INTRINSICS, None if bgrx is None else bgrx[j], mirror=True)
+        o.process(rec, 512, 424, R[j])
+        for k, v in o.counts().items():
+            assert int(res[j][k]) == v, (j, k)
+    ctx.close()
