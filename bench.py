@@ -266,6 +266,27 @@ def main():
     ms_e = timed(step_e2e, args.steps)
     e2e_val = Fe * world * args.steps / (ms_e / 1e3)
 
+    # the same frames entering as what the sensor delivers (uint16 depth in mm + registered colour, 6 B / pixel instead of 16):
+    # sp_process_depth_frames back-projects on the device (K2G::updateCloud), everything else is identical
+    import importlib
+    synth = importlib.import_module("stair_perception_b200.synth")
+    dframes = [synth.make_depth_frame(i) for i in range(N_DISTINCT)]
+    h_depth = torch.empty((Fe, H, W), dtype=torch.uint16).pin_memory()
+    h_bgrx = torch.empty((Fe, H, W, 4), dtype=torch.uint8).pin_memory()
+    for i in range(Fe):
+        h_depth[i].copy_(torch.from_numpy(dframes[i % N_DISTINCT][0]))
+        h_bgrx[i].copy_(torch.from_numpy(dframes[i % N_DISTINCT][1]))
+    res_d = np.zeros(Fe, dtype=sp.FRAME_DTYPE)
+
+    def step_depth():
+        ctx.process_depth_frames(h_depth, synth.INTRINSICS, bgrx=h_bgrx, mirror=True, R=h_R, nframes=Fe, results=res_d)
+
+    for _ in range(3):
+        step_depth()
+    ms_d = timed(step_depth, args.steps)
+    depth_val = Fe * world * args.steps / (ms_d / 1e3)
+    assert int(res_d["n_planes"].min()) >= 1 and int(res_d["status"].max()) == 0
+
     # sanity: the batch really produced planes
     assert int(results["n_planes"].min()) >= 1 and int(results["status"].max()) == 0, "unexpected empty results"
 
@@ -284,6 +305,9 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (F * N * 16 / 1e9), "parallelism": "frames sharded across %d GPU(s)" % world},
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 16 + 36)),
                     "d2h_bytes_per_step": int(Fe * sp.FRAME_DTYPE.itemsize), "frames_per_gpu_per_step": Fe, "ms_per_step": ms_e / args.steps},
+            "e2e_depth_input": {"value": depth_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 6 + 36)),
+                                "d2h_bytes_per_step": int(Fe * sp.FRAME_DTYPE.itemsize), "frames_per_gpu_per_step": Fe, "ms_per_step": ms_d / args.steps,
+                                "note": "same scenes entering as uint16 depth + registered colour (6 B/pixel) through sp_process_depth_frames"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_ingest_normals", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -162,6 +162,15 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
 int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
                    int32_t *max_pixel, int32_t *min_pixel);
 
+/* The step AFTER the path (host-side, no device work): the driver's hold-last-good filter and the 19-byte robot packet.
+ * sp_result_def = ResultDef (/root/reference/include/common.h:133-141).  sp_resolve_result replaces DProcessor::resolve_result
+ * (/root/reference/test/processor.cpp:46-82): inputs are the first step's height, depth, line.h and line.d in metres as the
+ * stair model reports them; each field of *result is overwritten only when the new value passes its range gate.
+ * sp_pack_robot replaces DProcessor::pack_and_send_robot (test/processor.cpp:85-100, test/processor.h:75-95). */
+typedef struct sp_result_def { int32_t has_stair; float height, width, v_height, v_depth; double time; } sp_result_def;
+void sp_resolve_result(sp_result_def *result, int has_stair, float step_height_m, float step_depth_m, float line_h_m, float line_d_m);
+int sp_pack_robot(const sp_result_def *result, uint8_t *out19);
+
 /* Timing of the last chunk: CUDA-event milliseconds per stage; returns number of stages written. */
 int sp_stage_ms(sp_ctx *ctx, float *out, int cap);
 const char *sp_stage_name(int i);

@@ -109,6 +109,30 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+class ResultDef(C.Structure):
+    """ResultDef, /root/reference/include/common.h:133-141"""
+    _fields_ = [("has_stair", C.c_int32), ("height", C.c_float), ("width", C.c_float), ("v_height", C.c_float), ("v_depth", C.c_float),
+                ("time", C.c_double)]
+
+
+def resolve_result(result, has_stair, step_height_m, step_depth_m, line_h_m, line_d_m):
+    """DProcessor::resolve_result (test/processor.cpp:46-82) on a ResultDef held across frames"""
+    L = lib()
+    L.sp_resolve_result.argtypes = [C.POINTER(ResultDef), C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.sp_resolve_result.restype = None
+    L.sp_resolve_result(C.byref(result), 1 if has_stair else 0, step_height_m, step_depth_m, line_h_m, line_d_m)
+    return result
+
+
+def pack_robot(result):
+    """the 19-byte packet of DProcessor::pack_and_send_robot (test/processor.cpp:85-100)"""
+    L = lib()
+    L.sp_pack_robot.argtypes = [C.POINTER(ResultDef), C.c_void_p]
+    buf = (C.c_uint8 * 19)()
+    assert L.sp_pack_robot(C.byref(result), buf) == 19
+    return bytes(buf)
+
+
 class SpError(RuntimeError):
     pass
 

@@ -729,6 +729,34 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
     return n;
 }
 
+/* DProcessor::resolve_result, /root/reference/test/processor.cpp:46-82: range-gated hold-last-good filter on the first step */
+void sp_resolve_result(sp_result_def *result, int has_stair, float step_height_m, float step_depth_m, float line_h_m, float line_d_m)
+{
+    if (!result) return;
+    result->has_stair = has_stair ? 1 : 0;
+    if (!has_stair) return;
+    const float height = step_height_m * 1000, width = step_depth_m * 1000, v_height = line_h_m * 1000, v_depth = line_d_m * 1000;
+    if (height > 80 && height < 150) result->height = height;
+    if (width > 250 && width < 330) result->width = width;
+    if (v_height > 700 && v_height < 1150) result->v_height = v_height;
+    if (v_depth > 0 && v_depth < 600) result->v_depth = v_depth;
+}
+
+/* DProcessor::pack_and_send_robot, test/processor.cpp:85-100 with the packed union of test/processor.h:75-95:
+ * { 0xFF, flag, v_depth, v_height, depth (= width), height, 0xFE }, little-endian floats, 19 bytes */
+int sp_pack_robot(const sp_result_def *result, uint8_t *out19)
+{
+    if (!result || !out19) return SP_ERR_ARG;
+    out19[0] = 0xFF;
+    out19[1] = (uint8_t)(result->has_stair ? 1 : 0);
+    memcpy(out19 + 2, &result->v_depth, 4);
+    memcpy(out19 + 6, &result->v_height, 4);
+    memcpy(out19 + 10, &result->width, 4);
+    memcpy(out19 + 14, &result->height, 4);
+    out19[18] = 0xFE;
+    return 19;
+}
+
 int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
                    int32_t *max_pixel, int32_t *min_pixel)
 {
