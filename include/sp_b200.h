@@ -162,6 +162,28 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
 int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
                    int32_t *max_pixel, int32_t *min_pixel);
 
+/* The consumer of the hand-off records: StairDetection::stairModel (StairPerception.cpp:1621-2773) restated without PCL,
+ * run on the host like the reference's (a few tens of planes), fed from the per-plane records of frame `frame` of the last
+ * chunk; the plane clouds stay on the device (findMinMaxProjPoint runs there as a reduction; only a merged ground plane
+ * pulls its points).  Returns SP_OK and fills *out: has_stair (what process() returns, StairPerception.cpp:190), the list
+ * nodes in order -- kind 0 = concave line, 1 = step with {height, depth, line.h, line.d} = the four columns of
+ * printStairEstParam (:265-290) -- and the final Plane::Ptype of every hand-off plane.  plane_h / plane_v index the frame's
+ * hand-off planes (-1 = merged ground plane, -2 = the virtual riser of a tread-to-tread pair).  Not restated: the two side
+ * planes and computePlaneCounter (:2861-3075), which only feed the GUI's contour drawing. */
+#define SP_MAX_STAIR_NODES 64
+typedef struct sp_stair_node {
+    int32_t kind, count, plane_h, plane_v;
+    float line_h, line_d, line_coeff[6];
+    double height, depth;
+} sp_stair_node;
+typedef struct sp_stair {
+    int32_t has_stair, n_steps, n_nodes;
+    int32_t ptype[SP_MAX_PLANES];
+    float vnormal[3], snormal[3];
+    sp_stair_node nodes[SP_MAX_STAIR_NODES];
+} sp_stair;
+int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out);
+
 /* The step AFTER the path (host-side, no device work): the driver's hold-last-good filter and the 19-byte robot packet.
  * sp_result_def = ResultDef (/root/reference/include/common.h:133-141).  sp_resolve_result replaces DProcessor::resolve_result
  * (/root/reference/test/processor.cpp:46-82): inputs are the first step's height, depth, line.h and line.d in metres as the

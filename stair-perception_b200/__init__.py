@@ -109,6 +109,12 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+STAIR_NODE_DTYPE = np.dtype([("kind", "<i4"), ("count", "<i4"), ("plane_h", "<i4"), ("plane_v", "<i4"), ("line_h", "<f4"), ("line_d", "<f4"),
+                             ("line_coeff", "<f4", (6,)), ("height", "<f8"), ("depth", "<f8")])
+STAIR_DTYPE = np.dtype([("has_stair", "<i4"), ("n_steps", "<i4"), ("n_nodes", "<i4"), ("ptype", "<i4", (SP_MAX_PLANES,)), ("vnormal", "<f4", (3,)),
+                        ("snormal", "<f4", (3,)), ("pad", "<i4"), ("nodes", STAIR_NODE_DTYPE, (64,))])
+
+
 class ResultDef(C.Structure):
     """ResultDef, /root/reference/include/common.h:133-141"""
     _fields_ = [("has_stair", C.c_int32), ("height", C.c_float), ("width", C.c_float), ("v_height", C.c_float), ("v_depth", C.c_float),
@@ -241,6 +247,15 @@ class Context:
                                           mn.ctypes.data, C.byref(pm), C.byref(pn)), "sp_minmax_proj")
         return mx, mn, int(pm.value), int(pn.value)
 
+    def stair_model(self, frame=0):
+        """StairDetection::stairModel on frame `frame` of the last chunk: returns a STAIR_DTYPE record; steps() lists
+        (height, depth, line.h, line.d) per step -- the columns of printStairEstParam"""
+        out = np.zeros(1, dtype=STAIR_DTYPE)
+        L = self.L
+        L.sp_stair_model.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self._check(L.sp_stair_model(self.h, frame, out.ctypes.data), "sp_stair_model")
+        return out[0]
+
     def stage_ms(self):
         arr = (C.c_float * 16)()
         n = self.L.sp_stage_ms(self.h, arr, 16)
@@ -305,3 +320,8 @@ class StairDetection:
         self.last_result = res
         self.last_context = ctx
         return int(res["n_planes"]) > 0, planes, res
+
+
+def stair_steps(stair):
+    """[(height, depth, V_Distance, H_Distance)] of a STAIR_DTYPE record, as StairDetection::printStairEstParam prints them"""
+    return [(float(n["height"]), float(n["depth"]), float(n["line_h"]), float(n["line_d"])) for n in stair["nodes"][:int(stair["n_nodes"])] if int(n["kind"]) == 1]

@@ -6,6 +6,7 @@
 #include "sp_front.cuh"
 #include "sp_seg.cuh"
 #include "sp_knn.cuh"
+#include "sp_stair.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -727,6 +728,61 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
         for (int i = 0; i < n; ++i) { xyz[3 * i] = a[idx[i]]; xyz[3 * i + 1] = b[idx[i]]; xyz[3 * i + 2] = c[idx[i]]; }
     }
     return n;
+}
+
+namespace {
+/* point access for the stair model: plane clouds stay on the device */
+struct DevicePoints : sp_stairmodel::StairPoints {
+    sp_ctx *ctx; int frame; const sp_frame_result *fr;
+    bool gather(int plane, std::vector<float> &xyz) override
+    {
+        if (plane < 0 || plane >= fr->n_planes) return false;
+        const SpDev &d = ctx->d; const size_t N = ctx->N, f = frame;
+        const int n = fr->planes[plane].count;
+        std::vector<int> idx((size_t)n);
+        if (n && cudaMemcpy(idx.data(), d.plane_idx + f * N + fr->planes[plane].first, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        if (hx.empty()) {
+            hx.resize(N); hy.resize(N); hz.resize(N);
+            if (cudaMemcpy(hx.data(), d.x + f * N, N * 4, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(hy.data(), d.y + f * N, N * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(hz.data(), d.z + f * N, N * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        }
+        for (int i = 0; i < n; ++i) { xyz.push_back(hx[(size_t)idx[(size_t)i]]); xyz.push_back(hy[(size_t)idx[(size_t)i]]); xyz.push_back(hz[(size_t)idx[(size_t)i]]); }
+        return true;
+    }
+    bool minmax(int plane, const float *c, const float *dir, float *max_xyz, float *min_xyz) override
+    {
+        if (plane < 0 || plane >= fr->n_planes || fr->planes[plane].count <= 0) return false;
+        const SpDev &d = ctx->d; const size_t N = ctx->N, f = frame;
+        const sp_plane_record &pr = fr->planes[plane];
+        k_minmax_proj<<<1, 256, 0, ctx->stream>>>(d, frame, pr.first, pr.count, c[0], c[1], c[2], dir[0], dir[1], dir[2], ctx->d_order);
+        ctx->launches += 1;
+        int ord[2] = { -1, -1 };
+        if (cudaMemcpyAsync(ord, ctx->d_order, sizeof(ord), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return false;
+        for (int w = 0; w < 2; ++w) {
+            float *xyz = w == 0 ? max_xyz : min_xyz;
+            if (ord[w] < 0) return false;
+            int pix = -1;
+            if (cudaMemcpy(&pix, d.plane_idx + f * N + pr.first + ord[w], 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+            if (cudaMemcpy(xyz, d.x + f * N + pix, 4, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(xyz + 1, d.y + f * N + pix, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(xyz + 2, d.z + f * N + pix, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        }
+        return true;
+    }
+    std::vector<float> hx, hy, hz;
+};
+} // namespace
+
+int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out)
+{
+    if (!ctx || !out || frame < 0 || frame >= ctx->last_nB) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<sp_frame_result> fr(1);
+    CK(cudaMemcpy(fr.data(), ctx->d.results + frame, sizeof(sp_frame_result), cudaMemcpyDeviceToHost));
+    DevicePoints pts; pts.ctx = ctx; pts.frame = frame; pts.fr = fr.data();
+    sp_stairmodel::stair_model(ctx->params, fr[0], pts, out);
+    return SP_OK;
 }
 
 /* DProcessor::resolve_result, /root/reference/test/processor.cpp:46-82: range-gated hold-last-good filter on the first step */

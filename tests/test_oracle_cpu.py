@@ -253,3 +253,37 @@ def test_determinism_and_thread_batch(sp, orc, synth):
     tot1, c1 = orc.process_batch(sp.DEFAULT_PARAMS, recs, 512, 424, Rs, nthreads=1)
     tot4, c4 = orc.process_batch(sp.DEFAULT_PARAMS, recs, 512, 424, Rs, nthreads=4)
     assert tot1 == tot4 and np.array_equal(c1, c4) and (c1 >= 8).all()
+
+
+PUBLISHED_0001 = [(0.110046, 0.280456, 0.490394, 0.526096), (0.110491, 0.276792, 0.397571, 0.807455),
+                  (0.111913, 0.269715, 0.300275, 1.08765), (0.104439, 0.283345, 0.212566, 1.35878)]
+
+
+def test_stair_model_reproduces_published_step_table(sp, oracles):
+    """The oracle's stair model (oracle/stair_model.py, a restatement of stairModel, StairPerception.cpp:1621-2773) on the
+    oracle's planes of samples/0001 finds the four steps of pic/screenshot2.png: 14 of the 16 published numbers within 0.5 mm,
+    all within 1.6 mm (the first step hangs on a 330-point riser)."""
+    from oracle import stair_model as sm
+    o = oracles["0001"]
+    res = sm.stair_model(sp.DEFAULT_PARAMS, o.tap("planes"), o.tap("xyz"), o.tap("plane_idx"))
+    assert res["has_stair"] and len(res["steps"]) == 4
+    err = np.abs(np.array(res["steps"]) - np.array(PUBLISHED_0001))
+    assert err.max() < 1.6e-3 and (err < 0.5e-3).sum() >= 14, err
+    assert err[1:, :2].max() < 1e-3                    # heights and depths of steps 2-4: the 1 mm north-star tolerance
+    o0 = oracles["0000"]
+    res0 = sm.stair_model(sp.DEFAULT_PARAMS, o0.tap("planes"), o0.tap("xyz"), o0.tap("plane_idx"))
+    assert res0["has_stair"] and len(res0["steps"]) == 2
+
+
+def test_stair_model_on_synthetic_ground_truth(sp, orc, synth):
+    """synthetic frames have a known staircase: rise 0.11 m, run 0.28 m"""
+    from oracle import stair_model as sm
+    for fid in (0, 3):
+        rec, R = synth.make_frame(fid)
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(rec, 512, 424, R)
+        res = sm.stair_model(sp.DEFAULT_PARAMS, o.tap("planes"), o.tap("xyz"), o.tap("plane_idx"))
+        assert res["has_stair"] and len(res["steps"]) >= 2
+        steps = np.array(res["steps"])
+        assert np.abs(steps[:, 0] - 0.11).max() < 3e-3
+        assert np.abs(steps[:-1, 1] - 0.28).max() < 3e-3

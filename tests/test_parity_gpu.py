@@ -270,3 +270,25 @@ def test_depth_image_ingest(sp, orc, synth, dtype, with_colour):
         for k, v in o.counts().items():
             assert int(res[j][k]) == v, (j, k)
     ctx.close()
+
+
+def test_stair_model_matches_oracle_and_published_table(sp, orc, synth, samples, ctx1):
+    """next-row f1: sp_stair_model (stairModel restated in C++ over the hand-off records, plane clouds left on the device)
+    against the independent numpy restatement in oracle/stair_model.py, and against pic/screenshot2.png for samples/0001"""
+    from oracle import stair_model as sm
+    cases = [(samples["0001"][0], None), (samples["0000"][0], None)] + [synth.make_frame(f) for f in (0, 3, 7)]
+    for rec, R in cases:
+        res = ctx1.process_frames(rec, None if R is None else R.reshape(1, 9))[0]
+        st = ctx1.stair_model(0)
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(rec, 512, 424, R)
+        want = sm.stair_model(sp.DEFAULT_PARAMS, o.tap("planes"), o.tap("xyz"), o.tap("plane_idx"))
+        got = sp.stair_steps(st)
+        assert bool(st["has_stair"]) == bool(want["has_stair"]) and len(got) == len(want["steps"])
+        assert np.allclose(np.array(got), np.array(want["steps"]), rtol=0, atol=2e-6), (got, want["steps"])
+        assert list(st["ptype"][:int(res["n_planes"])]) == want["ptype"]
+    res = ctx1.process_frames(samples["0001"][0])[0]
+    got = np.array(sp.stair_steps(ctx1.stair_model(0)))
+    published = np.array([(0.110046, 0.280456, 0.490394, 0.526096), (0.110491, 0.276792, 0.397571, 0.807455),
+                          (0.111913, 0.269715, 0.300275, 1.08765), (0.104439, 0.283345, 0.212566, 1.35878)])
+    assert got.shape == (4, 4) and np.abs(got - published).max() < 1.6e-3 and np.abs(got - published)[1:, :2].max() < 1e-3
