@@ -47,12 +47,21 @@ int main(int argc, char **argv)
     std::vector<Plane> vector_plane_sorted;
     try {
         StairDetection stair_detection(sp_b200::default_parameters());          // a new object per frame, as test/processor.cpp:156
-        const bool has = stair_detection.process(cloud_in, mode, vector_plane_sorted, cloud_show, normal_show);
+        sp_stair stair_model;
+        const bool has_stair = stair_detection.process(cloud_in, mode, vector_plane_sorted, cloud_show, normal_show, nullptr, &stair_model);
+        const bool has = mode == stair ? !vector_plane_sorted.empty() : false;
         std::printf("has_planes %d planes %zu cloud_show %zu\n", has ? 1 : 0, vector_plane_sorted.size(), cloud_show.points.size());
         for (const Plane &p : vector_plane_sorted) {
             std::printf("%d %zu", (int)p.type, p.cloud.points.size());
             for (size_t k = 0; k < p.coefficients.values.size(); ++k) std::printf(" %a", (double)p.coefficients.values[k]);
             std::printf(" %a %a %a\n", (double)p.center.x, (double)p.center.y, (double)p.center.z);
+        }
+        if (mode == stair) {
+            // StairDetection::printStairEstParam, StairPerception.cpp:265-290
+            std::printf("stair %d steps %d\nHeight\t\tDepth\t\tV_Distance\tH_Distance\n", has_stair ? 1 : 0, stair_model.n_steps);
+            for (int i = 0; i < stair_model.n_nodes; ++i)
+                if (stair_model.nodes[i].kind == 1)
+                    std::printf("%g\t%g\t%g\t%g\n", stair_model.nodes[i].height, stair_model.nodes[i].depth, (double)stair_model.nodes[i].line_h, (double)stair_model.nodes[i].line_d);
         }
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

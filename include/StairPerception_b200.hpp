@@ -10,10 +10,10 @@
  * unchanged against the reference's own types: define SP_B200_REFERENCE_TYPES and include the reference's
  * include/common.h first (PCL is absent from this image, so that variant is not compiled here).
  *
- * What process() does NOT do: run the stair model.  `stairModel()` / `computePlaneCounter()`
- * (StairPerception.cpp:1621-2773, :2861-3075) are the unchanged consumer of `vector_plane_sorted`; in a drop-in the
- * reference keeps calling its own (INTEGRATION.md shows the 12-line patch).  process() here returns "planes were
- * handed over" instead of "stair found".
+ * The stair model: `stairModel()` / `computePlaneCounter()` (StairPerception.cpp:1621-2773, :2861-3075) are the unchanged
+ * consumer of `vector_plane_sorted`; in a drop-in the reference keeps calling its own (INTEGRATION.md shows the patch) and
+ * process() returns "planes were handed over".  Stand-alone callers pass `stair_out`: process() then also runs the
+ * library's restatement of stairModel (sp_stair_model) and returns "stair found" like the reference.
  *
  * The reference constructs a StairDetection per frame (test/processor.cpp:156); all device state therefore lives in
  * a process-level context per (device, width, height), created on first use and shared by every object.
@@ -149,8 +149,10 @@ public:
      * stair model writes.  `rotation` (optional, 9 floats row-major) applies rotationCloudPoints (test/reader.cpp:273-324)
      * on the device before everything else; NULL = cloud already levelled. */
     bool process(const pcl::PointCloud<PointType> &cloud_in, const ShowModeDef show_mode, std::vector<Plane> &vector_plane_sorted,
-                 pcl::PointCloud<PointType> &cloud_show, pcl::PointCloud<pcl::Normal> &normal_show, const float *rotation = nullptr)
+                 pcl::PointCloud<PointType> &cloud_show, pcl::PointCloud<pcl::Normal> &normal_show, const float *rotation = nullptr,
+                 sp_stair *stair_out = nullptr)
     {
+        if (stair_out) std::memset(stair_out, 0, sizeof(*stair_out));
         if (show_mode == original) return false;                       /* StairPerception.cpp:24 */
         if (cloud_in.points.empty()) return false;                     /* :27 */
         const int W = cloud_in.width ? (int)cloud_in.width : (int)cloud_in.points.size();
@@ -280,6 +282,13 @@ public:
             plane.type = r.type == 1 ? Plane::horizontal : Plane::vertical;
             plane.ptype = Plane::others;                                /* :1448 */
             vector_plane_sorted.push_back(plane);
+        }
+        if (stair_out) {
+            /* the library's own restatement of stairModel (StairPerception.cpp:1621-2773): process() then answers
+             * "stair found" exactly like the reference (:190) */
+            if (sp_stair_model(ctx, 0, stair_out) != SP_OK) throw std::runtime_error(std::string("sp_stair_model failed: ") + sp_last_error(ctx));
+            for (int i = 0; i < last_.n_planes && i < (int)vector_plane_sorted.size(); ++i) vector_plane_sorted[(size_t)i].ptype = (Plane::Ptype)stair_out->ptype[i];
+            return stair_out->has_stair != 0;
         }
         return last_.n_planes > 0;
     }

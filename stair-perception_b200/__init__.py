@@ -319,7 +319,12 @@ class StairDetection:
             planes.append({"record": rec, "xyz": xyz, "pixel_idx": idx})
         self.last_result = res
         self.last_context = ctx
-        return int(res["n_planes"]) > 0, planes, res
+        self.last_stair = None
+        if show_mode == SHOW["stair"] and int(res["n_planes"]) > 0:
+            # the reference's process() answers "stair found" (StairPerception.cpp:190)
+            self.last_stair = ctx.stair_model(0)
+            return bool(self.last_stair["has_stair"]), planes, res
+        return False, planes, res
 
 
 def stair_steps(stair):
