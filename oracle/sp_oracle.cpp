@@ -113,7 +113,7 @@ void normals_integral(orc_ctx *c)
     const int W = c->W, H = c->H, N = c->N;
     const float *X = c->x.data(), *Y = c->y.data(), *Z = c->z.data();
     c->nx.assign(N, kNaN); c->ny.assign(N, kNaN); c->nz.assign(N, kNaN);
-    if (W < 12 || H < 12) return;
+    if (W < 3 || H < 3) return;                      /* nothing can lie 5 pixels inside the border; the loops below need 3 x 3 */
 
     /* depth-change map (on the levelled z = lateral axis: the reference's quirk) */
     std::vector<uint8_t> dcm(N, 255);

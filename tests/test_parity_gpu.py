@@ -292,3 +292,23 @@ def test_stair_model_matches_oracle_and_published_table(sp, orc, synth, samples,
     published = np.array([(0.110046, 0.280456, 0.490394, 0.526096), (0.110491, 0.276792, 0.397571, 0.807455),
                           (0.111913, 0.269715, 0.300275, 1.08765), (0.104439, 0.283345, 0.212566, 1.35878)])
     assert got.shape == (4, 4) and np.abs(got - published).max() < 1.6e-3 and np.abs(got - published)[1:, :2].max() < 1e-3
+
+
+@pytest.mark.parametrize("w,h", [(200, 150), (97, 61), (33, 13), (512, 11)])
+def test_other_image_sizes(sp, orc, samples, w, h):
+    """the path is not tied to 512 x 424: windows cut from a recorded frame, widths that are not a multiple of the tile, an
+    image too small for any normal (PCL needs more than 10 rows), all against the oracle"""
+    rec, W0, H0 = samples["0001"]
+    img = rec.reshape(H0, W0)
+    c0 = min(200, W0 - w)
+    sub = np.ascontiguousarray(img[120:120 + h, c0:c0 + w]).reshape(-1)
+    p = dict(sp.DEFAULT_PARAMS)
+    p.update(seg_rest_point=60, min_cluster_size=5)
+    ctx = sp.Context(p, device=0, width=w, height=h, max_batch=2)
+    res = ctx.process_frames(np.stack([sub, sub]))
+    o = orc.Oracle(p)
+    o.process(sub, w, h)
+    for f in (0, 1):
+        bad = compare_frame(ctx, f, res[f], o)
+        assert not bad, "\n".join(bad[:20])
+    ctx.close()
