@@ -35,7 +35,10 @@ struct K1Smem {
     unsigned char zero[K1_FH * K1_FW];
     unsigned char hd[K1_FH * K1_TW];
     unsigned char fx[K1_GH * K1_GW], fy[K1_GH * K1_GW];
-    int red[8];
+    float onx[K1_TH * K1_TW], ony[K1_TH * K1_TW], onz[K1_TH * K1_TW];   /* normals of the tile, stored coalesced at the end */
+    unsigned short list[K1_TH * K1_TW];   /* pixels that get a normal: 5 x 5 windows from the front, smaller ones from the back */
+    int n5, nsmall;
+    int red[6];
 };
 
 __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
@@ -155,65 +158,118 @@ __global__ void __launch_bounds__(K1_THREADS) k_ingest_normals(SpDev d)
     }
     __syncthreads();
 
-    /* S3 + S5: smoothing size and normal per owned pixel */
-    /* kcat[a][h]: rect size implied by a flagged pixel at row distance a, column distance h
+    /* S3: smoothing size per owned pixel.  Pixels without a normal (invalid, border, next to a depth discontinuity) are
+     * about a third of the tile: the pixels that do get one are compacted into a list first, so that the box sums below run
+     * with full warps.  kcat[a][h]: rect size implied by a flagged pixel at row distance a, column distance h
      * (chamfer 1.0/1.4: d = 1.4*min + (max-min); d<=2 -> 0 (NaN), (2,3) -> 2, [3,4) -> 3, [4,5) -> 4, >=5 -> 5) */
+    if (tid == 0) { s.n5 = 0; s.nsmall = 0; }
+    __syncthreads();
     const unsigned kcat0 = 0x543000u, kcat1 = 0x543200u, kcat2 = 0x543220u, kcat3 = 0x554333u, kcat4 = 0x555444u;
     for (int e = tid; e < K1_TH * K1_TW; e += K1_THREADS) {
         const int rr = e / K1_TW, cc = e - rr * K1_TW;
         const int gr = r0 + rr, gc = c0 + cc;
-        if (gr >= H || gc >= W) continue;
-        float onx = qnan, ony = qnan, onz = qnan;
-        const int se = (rr + K1_HALO) * K1_RW + cc + K1_HALO;
-        const float px = s.sx[se], py = s.sy[se], pz = s.sz[se];
-        if (gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(pz)) {
-            int k = 5;
-            {
-                const unsigned char *col = &s.hd[(rr + 4) * K1_TW + cc];
-                k = min(k, (int)((kcat0 >> (4 * col[0])) & 15u));
-                k = min(k, (int)((kcat1 >> (4 * col[-K1_TW])) & 15u));
-                k = min(k, (int)((kcat1 >> (4 * col[K1_TW])) & 15u));
-                k = min(k, (int)((kcat2 >> (4 * col[-2 * K1_TW])) & 15u));
-                k = min(k, (int)((kcat2 >> (4 * col[2 * K1_TW])) & 15u));
-                k = min(k, (int)((kcat3 >> (4 * col[-3 * K1_TW])) & 15u));
-                k = min(k, (int)((kcat3 >> (4 * col[3 * K1_TW])) & 15u));
-                k = min(k, (int)((kcat4 >> (4 * col[-4 * K1_TW])) & 15u));
-                k = min(k, (int)((kcat4 >> (4 * col[4 * K1_TW])) & 15u));
-            }
-            if (k >= 2) {
-                const int half = k >> 1;
-                const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
-                double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
-                int cntx = 0, cnty = 0;
-                for (int a = 0; a < k; ++a) {
-                    double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
-                    const int gb = g0 + a * K1_GW;
-                    for (int b = 0; b < k; ++b) {
-                        const int ge = gb + b;
-                        rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
-                        ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
-                        cntx += s.fx[ge]; cnty += s.fy[ge];
-                    }
-                    sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
-                }
-                if (cntx != 0 && cnty != 0) {
-                    const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
-                    const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
-                    const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
-                    const double L = n0 * n0 + (n1 * n1 + n2 * n2);
-                    if (L != 0.0) {
-                        const double sq = sqrt(L);
-                        float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
-                        const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
-                        const float cs = (vx * fx + vy * fy + vz * fz);
-                        if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
-                        onx = fx; ony = fy; onz = fz;
-                    }
-                }
+        s.onx[e] = qnan; s.ony[e] = qnan; s.onz[e] = qnan;
+        int k = 0;
+        if (gr < H && gc < W && gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO])) {
+            const unsigned char *col = &s.hd[(rr + 4) * K1_TW + cc];
+            k = 5;
+            k = min(k, (int)((kcat0 >> (4 * col[0])) & 15u));
+            k = min(k, (int)((kcat1 >> (4 * col[-K1_TW])) & 15u));
+            k = min(k, (int)((kcat1 >> (4 * col[K1_TW])) & 15u));
+            k = min(k, (int)((kcat2 >> (4 * col[-2 * K1_TW])) & 15u));
+            k = min(k, (int)((kcat2 >> (4 * col[2 * K1_TW])) & 15u));
+            k = min(k, (int)((kcat3 >> (4 * col[-3 * K1_TW])) & 15u));
+            k = min(k, (int)((kcat3 >> (4 * col[3 * K1_TW])) & 15u));
+            k = min(k, (int)((kcat4 >> (4 * col[-4 * K1_TW])) & 15u));
+            k = min(k, (int)((kcat4 >> (4 * col[4 * K1_TW])) & 15u));
+        }
+        /* warp-aggregated appends: one shared atomic per warp and list */
+        const unsigned lanebit = 1u << (tid & 31), lt = lanebit - 1u;
+        const unsigned b5 = __ballot_sync(0xffffffffu, k == 5), bs = __ballot_sync(0xffffffffu, k >= 2 && k < 5);
+        if (b5) {
+            int base = 0;
+            if ((b5 & lt) == 0 && (b5 & lanebit)) base = atomicAdd(&s.n5, __popc(b5));
+            base = __shfl_sync(0xffffffffu, base, __ffs(b5) - 1);
+            if (k == 5) s.list[base + __popc(b5 & lt)] = (unsigned short)e;
+        }
+        if (bs) {
+            int base = 0;
+            if ((bs & lt) == 0 && (bs & lanebit)) base = atomicAdd(&s.nsmall, __popc(bs));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bs) - 1);
+            if (k >= 2 && k < 5) s.list[K1_TH * K1_TW - 1 - (base + __popc(bs & lt))] = (unsigned short)(e | (k << 12));
+        }
+    }
+    __syncthreads();
+    /* S5: box sums + normal.  Sum order (the oracle's): rows top to bottom of (row sums left to right), all in double. */
+    auto finish = [&](int e, double sgx0, double sgx1, double sgx2, double sgy0, double sgy1, double sgy2, int cntx, int cnty) {
+        if (cntx != 0 && cnty != 0) {
+            const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
+            const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
+            const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
+            const double L = n0 * n0 + (n1 * n1 + n2 * n2);
+            if (L != 0.0) {
+                const int rr = e / K1_TW, cc = e - rr * K1_TW;
+                const int se = (rr + K1_HALO) * K1_RW + cc + K1_HALO;
+                const float px = s.sx[se], py = s.sy[se], pz = s.sz[se];
+                const double sq = sqrt(L);
+                float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
+                const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
+                const float cs = (vx * fx + vy * fy + vz * fz);
+                if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
+                s.onx[e] = fx; s.ony[e] = fy; s.onz[e] = fz;
             }
         }
+    };
+    const int n5 = s.n5, nsmall = s.nsmall;
+    for (int i = tid; i < n5; i += K1_THREADS) {                 /* the 5 x 5 windows: fixed trip counts */
+        const int e = s.list[i];
+        const int rr = e / K1_TW, cc = e - rr * K1_TW;
+        const int g0 = rr * K1_GW + cc;                          /* (rr + 2 - 2, cc + 2 - 2) */
+        double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
+        int cntx = 0, cnty = 0;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
+            const int gb = g0 + a * K1_GW;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                const int ge = gb + b;
+                rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
+                ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
+                cntx += s.fx[ge]; cnty += s.fy[ge];
+            }
+            sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
+        }
+        finish(e, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2, cntx, cnty);
+    }
+    for (int i = tid; i < nsmall; i += K1_THREADS) {             /* windows of 2, 3, 4 */
+        const int code = s.list[K1_TH * K1_TW - 1 - i];
+        const int e = code & 0xfff, k = code >> 12;
+        const int rr = e / K1_TW, cc = e - rr * K1_TW;
+        const int half = k >> 1;
+        const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
+        double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
+        int cntx = 0, cnty = 0;
+        for (int a = 0; a < k; ++a) {
+            double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
+            const int gb = g0 + a * K1_GW;
+            for (int b = 0; b < k; ++b) {
+                const int ge = gb + b;
+                rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
+                ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
+                cntx += s.fx[ge]; cnty += s.fy[ge];
+            }
+            sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
+        }
+        finish(e, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2, cntx, cnty);
+    }
+    __syncthreads();
+    for (int e = tid; e < K1_TH * K1_TW; e += K1_THREADS) {
+        const int rr = e / K1_TW, cc = e - rr * K1_TW;
+        const int gr = r0 + rr, gc = c0 + cc;
+        if (gr >= H || gc >= W) continue;
         const size_t gi = (size_t)f * N + (size_t)gr * W + gc;
-        d.nx[gi] = onx; d.ny[gi] = ony; d.nz[gi] = onz;
+        d.nx[gi] = s.onx[e]; d.ny[gi] = s.ony[e]; d.nz[gi] = s.onz[e];
     }
 }
 
