@@ -121,7 +121,7 @@ __device__ __forceinline__ void sp_uf_unite(int *parent, int a, int b)
  * time, so the (divergent, pointer-chasing) union-find code always runs with a full warp. */
 __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
 {
-    __shared__ int2 queue[8][64];
+    __shared__ int2 queue[8][96];
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = (size_t)s * d.N;
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
@@ -145,23 +145,35 @@ __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
                 const unsigned h = k == 13 ? h0 : (sp_cell_hash(a + da, b + db, c + dc) & ((1u << SP_HASH_BITS) - 1u));
                 j = start[h]; j1 = start[h + 1];
             }
-            while (__any_sync(0xffffffffu, j < j1)) {
-                bool hit = false; int oj = 0;
+            const int own_limit = k == 13 ? oi : 0x7fffffff;             /* own cell: only members with a smaller list position */
+            const int trips = __reduce_max_sync(0xffffffffu, j1 - j);     /* warp-uniform trip count */
+            for (int it = 0; it < trips; it += 2) {
+                bool hit0 = false, hit1 = false; int oj0 = 0, oj1 = 0;
                 if (j < j1) {
                     const float4 qq = sp[j];
-                    oj = __float_as_int(qq.w);
+                    oj0 = __float_as_int(qq.w);
                     const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
                     float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
-                    hit = dist < r2 && !(k == 13 && oj >= oi);
-                    if (hit) hit = parent[oi] != parent[oj];
-                    ++j;
+                    hit0 = dist < r2 && oj0 < own_limit;
                 }
-                const unsigned bm = __ballot_sync(0xffffffffu, hit);
-                if (bm) {
-                    if (hit) q[qn + __popc(bm & lt)] = make_int2(oi, oj);
-                    qn += __popc(bm);
+                if (j + 1 < j1) {
+                    const float4 qq = sp[j + 1];
+                    oj1 = __float_as_int(qq.w);
+                    const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
+                    float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;
+                    hit1 = dist < r2 && oj1 < own_limit;
+                }
+                j += 2;
+                if (hit0) hit0 = parent[oi] != parent[oj0];
+                if (hit1) hit1 = parent[oi] != parent[oj1];
+                const unsigned b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
+                if (b0 | b1) {
+                    if (hit0) q[qn + __popc(b0 & lt)] = make_int2(oi, oj0);
+                    qn += __popc(b0);
+                    if (hit1) q[qn + __popc(b1 & lt)] = make_int2(oi, oj1);
+                    qn += __popc(b1);
                     __syncwarp();
-                    if (qn >= 32) {
+                    while (qn >= 32) {
                         const int2 e = q[qn - 32 + lane];
                         qn -= 32;
                         __syncwarp();
