@@ -36,6 +36,19 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def load_traffic(kernel, frames_per_launch):
+    """dram bytes of one launch from the committed ncu capture (profiles/r01_traffic.json), or None"""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if t["kernel"] == kernel and int(t["frames_per_launch"]) == int(frames_per_launch):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -316,7 +329,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_ingest_normals", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "ms_per_launch": k1, "frames_per_launch": nb,
+                         "traffic": load_traffic("k_ingest_normals", nb), "peak_source": peak_src, "ms_per_launch": k1, "frames_per_launch": nb,
                          "algorithmic_bytes_per_launch": K1K2_BYTES_PER_POINT * N * nb},
             "stage_ms_last_chunk": stage_full, "voxel_stage_ms": float(np.mean(vox_ms)),
             "cpu_baseline": cpu,
