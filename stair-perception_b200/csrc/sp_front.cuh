@@ -21,24 +21,26 @@
 #define K1_TW 32
 #define K1_TH 32
 #define K1_HALO 5
-#define K1_RW (K1_TW + 2 * K1_HALO)      /* 42 */
+#define K1_RW (K1_TW + 2 * K1_HALO)      /* z region: halo 5 (42) */
 #define K1_RH (K1_TH + 2 * K1_HALO)
+#define K1_XW (K1_TW + 6)                /* x, y region: halo 3 (gradients at halo 2 need +-1) */
+#define K1_XH (K1_TH + 6)
 #define K1_FW (K1_TW + 8)                /* zero-flag region: halo 4 */
 #define K1_FH (K1_TH + 8)
 #define K1_GW (K1_TW + 4)                /* gradient region: halo 2 */
 #define K1_GH (K1_TH + 4)
 #define K1_THREADS 256
 
-struct K1Smem {
-    float sx[K1_RH * K1_RW], sy[K1_RH * K1_RW], sz[K1_RH * K1_RW];
+struct K1Smem {                           /* 54.7 KB: four CTAs per SM */
+    float sz[K1_RH * K1_RW];
+    float sx[K1_XH * K1_XW], sy[K1_XH * K1_XW];
     float gx[3][K1_GH * K1_GW], gy[3][K1_GH * K1_GW];
     unsigned char zero[K1_FH * K1_FW];
     unsigned char hd[K1_FH * K1_TW];
-    unsigned char fx[K1_GH * K1_GW], fy[K1_GH * K1_GW];
-    float onx[K1_TH * K1_TW], ony[K1_TH * K1_TW], onz[K1_TH * K1_TW];   /* normals of the tile, stored coalesced at the end */
-    unsigned short list[K1_TH * K1_TW];   /* pixels that get a normal: 5 x 5 windows from the front, smaller ones from the back */
-    int n5, nsmall;
-    int red[6];
+    unsigned char fl[K1_GH * K1_GW];      /* finite flags of the gradient elements: bit 0 = dx, bit 1 = dy */
+    unsigned short list[K1_TH * K1_TW];   /* pixels that get a normal, by window size: 5 from the front, 4 from the back */
+    unsigned short list2[K1_TH * K1_TW / 2];   /* windows of 3 and 2, tagged (pixel | k << 12); a tile with more takes them in place */
+    int n5, n4, n32, pad;
 };
 
 __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
@@ -48,7 +50,51 @@ __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
     return (fabsf(za - zb) > thr) || !sp_finite(za) || !sp_finite(zb);
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k_ingest_normals(SpDev d)
+/* k x k box sums of the two gradient fields around tile pixel e, in the oracle's order (rows top to bottom of row sums
+ * left to right, double), then cross product, normalisation and flip; stores the normal straight to global memory */
+template <int K>
+__device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e, size_t tile_base, int W)
+{
+    const int rr = e / K1_TW, cc = e - rr * K1_TW;
+    const int half = K >> 1;
+    const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
+    double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
+    unsigned orf = 0;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
+        const int gb = g0 + a * K1_GW;
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            const int ge = gb + b;
+            rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
+            ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
+            orf |= s.fl[ge];
+        }
+        sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
+    }
+    float onx = __int_as_float(0x7fc00000), ony = onx, onz = onx;
+    if (orf == 3u) {                                   /* both windows hold at least one finite element */
+        const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
+        const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
+        const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
+        const double L = n0 * n0 + (n1 * n1 + n2 * n2);
+        if (L != 0.0) {
+            const int sxe = (rr + 3) * K1_XW + cc + 3;
+            const float px = s.sx[sxe], py = s.sy[sxe], pz = s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO];
+            const double sq = sqrt(L);
+            float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
+            const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
+            const float cs = (vx * fx + vy * fy + vz * fz);
+            if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
+            onx = fx; ony = fy; onz = fz;
+        }
+    }
+    const size_t gi = tile_base + (size_t)rr * W + cc;
+    d.nx[gi] = onx; d.ny[gi] = ony; d.nz[gi] = onz;
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
 {
     extern __shared__ __align__(16) unsigned char k1_raw[];
     K1Smem &s = *reinterpret_cast<K1Smem *>(k1_raw);
@@ -63,65 +109,61 @@ __global__ void __launch_bounds__(K1_THREADS) k_ingest_normals(SpDev d)
         for (int i = 0; i < 9; ++i) R[i] = __ldg(d.R + 9 * f + i);
     }
     const float qnan = __int_as_float(0x7fc00000);
+    if (tid == 0) { s.n5 = 0; s.n4 = 0; s.n32 = 0; }
 
-    /* S0: load tile + halo, level, mask */
-    for (int e = tid; e < K1_RH * K1_RW; e += K1_THREADS) {
-        const int rr = e / K1_RW, cc = e - rr * K1_RW;
-        const int gr = r0 - K1_HALO + rr, gc = c0 - K1_HALO + cc;
-        float ox = qnan, oy = qnan, oz = qnan;
-        if (gr >= 0 && gr < H && gc >= 0 && gc < W) {
-            const float4 p = __ldg(in + (size_t)gr * W + gc);
-            ox = p.x; oy = p.y; oz = p.z;
-            if (rot) {
-                if (!isnan(p.x)) {
-                    ox = R[0] * p.x + R[1] * p.y + R[2] * p.z;
-                    oy = R[3] * p.x + R[4] * p.y + R[5] * p.z;
-                    oz = R[6] * p.x + R[7] * p.y + R[8] * p.z;
-                } else { ox = oy = oz = qnan; }
-            }
-            const unsigned rgba = __float_as_uint(p.w);
-            if ((rgba & 255u) == 0u || ((rgba >> 8) & 255u) == 0u || ((rgba >> 16) & 255u) == 0u) { ox = oy = oz = qnan; }
-        }
-        s.sx[e] = ox; s.sy[e] = oy; s.sz[e] = oz;
-    }
-    __syncthreads();
-
-    /* owned pixels: write levelled xyz, crop predicate, bounding box, counts */
+    /* S0: load tile + halo, level, mask; the owned pixels also go out (levelled xyz) and into the crop statistics */
     {
-        int mnx = 0x7fffffff, mny = 0x7fffffff, mnz = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000, mxz = (int)0x80000000;
+        float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
         int nvalid = 0, ncrop = 0;
-        for (int e = tid; e < K1_TH * K1_TW; e += K1_THREADS) {
-            const int rr = e / K1_TW, cc = e - rr * K1_TW;
-            const int gr = r0 + rr, gc = c0 + cc;
-            if (gr < H && gc < W) {
-                const int se = (rr + K1_HALO) * K1_RW + cc + K1_HALO;
-                const float px = s.sx[se], py = s.sy[se], pz = s.sz[se];
+        for (int e = tid; e < K1_RH * K1_RW; e += K1_THREADS) {
+            const int rr = e / K1_RW, cc = e - rr * K1_RW;
+            const int gr = r0 - K1_HALO + rr, gc = c0 - K1_HALO + cc;
+            float ox = qnan, oy = qnan, oz = qnan;
+            const bool inside = gr >= 0 && gr < H && gc >= 0 && gc < W;
+            if (inside) {
+                const float4 p = __ldg(in + (size_t)gr * W + gc);
+                ox = p.x; oy = p.y; oz = p.z;
+                if (rot) {
+                    if (!isnan(p.x)) {
+                        ox = R[0] * p.x + R[1] * p.y + R[2] * p.z;
+                        oy = R[3] * p.x + R[4] * p.y + R[5] * p.z;
+                        oz = R[6] * p.x + R[7] * p.y + R[8] * p.z;
+                    } else { ox = oy = oz = qnan; }
+                }
+                const unsigned rgba = __float_as_uint(p.w);
+                if ((rgba & 255u) == 0u || ((rgba >> 8) & 255u) == 0u || ((rgba >> 16) & 255u) == 0u) { ox = oy = oz = qnan; }
+            }
+            s.sz[e] = oz;
+            const int xr = rr - 2, xc = cc - 2;                                  /* x, y keep a halo of 3 */
+            if (xr >= 0 && xr < K1_XH && xc >= 0 && xc < K1_XW) { s.sx[xr * K1_XW + xc] = ox; s.sy[xr * K1_XW + xc] = oy; }
+            const int tr = rr - K1_HALO, tc = cc - K1_HALO;
+            if (inside && tr >= 0 && tr < K1_TH && tc >= 0 && tc < K1_TW) {       /* owned pixel */
                 const size_t gi = (size_t)f * N + (size_t)gr * W + gc;
-                d.x[gi] = px; d.y[gi] = py; d.z[gi] = pz;
-                if (sp_finite3(px, py, pz)) {
+                d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz;
+                if (sp_finite3(ox, oy, oz)) {
                     ++nvalid;
-                    if (!(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
+                    if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {
                         ++ncrop;
-                        const int ox = sp_f2ord(px), oy = sp_f2ord(py), oz = sp_f2ord(pz);
-                        mnx = min(mnx, ox); mny = min(mny, oy); mnz = min(mnz, oz);
-                        mxx = max(mxx, ox); mxy = max(mxy, oy); mxz = max(mxz, oz);
+                        mnx = fminf(mnx, ox); mny = fminf(mny, oy); mnz = fminf(mnz, oz);
+                        mxx = fmaxf(mxx, ox); mxy = fmaxf(mxy, oy); mxz = fmaxf(mxz, oz);
                     }
                 }
             }
         }
-        mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny); mnz = __reduce_min_sync(0xffffffffu, mnz);
-        mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy); mxz = __reduce_max_sync(0xffffffffu, mxz);
         nvalid = __reduce_add_sync(0xffffffffu, nvalid); ncrop = __reduce_add_sync(0xffffffffu, ncrop);
-        if ((tid & 31) == 0 && nvalid) {
-            atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
-            if (ncrop) {
+        if (__any_sync(0xffffffffu, ncrop != 0)) {
+            const int a0 = __reduce_min_sync(0xffffffffu, sp_f2ord(mnx)), a1 = __reduce_min_sync(0xffffffffu, sp_f2ord(mny)), a2 = __reduce_min_sync(0xffffffffu, sp_f2ord(mnz));
+            const int b0 = __reduce_max_sync(0xffffffffu, sp_f2ord(mxx)), b1 = __reduce_max_sync(0xffffffffu, sp_f2ord(mxy)), b2 = __reduce_max_sync(0xffffffffu, sp_f2ord(mxz));
+            if ((tid & 31) == 0 && ncrop) {
                 atomicAdd(&d.counts[f * SP_NCOUNT + 2], ncrop);
                 int *mm = d.mm + f * 8;
-                atomicMin(mm + 0, mnx); atomicMin(mm + 1, mny); atomicMin(mm + 2, mnz);
-                atomicMax(mm + 3, mxx); atomicMax(mm + 4, mxy); atomicMax(mm + 5, mxz);
+                atomicMin(mm + 0, a0); atomicMin(mm + 1, a1); atomicMin(mm + 2, a2);
+                atomicMax(mm + 3, b0); atomicMax(mm + 4, b1); atomicMax(mm + 5, b2);
             }
         }
+        if ((tid & 31) == 0 && nvalid) atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
     }
+    __syncthreads();
 
     /* S1: depth-change flags on the lateral coordinate z (reference quirk), halo 4 */
     for (int e = tid; e < K1_FH * K1_FW; e += K1_THREADS) {
@@ -135,13 +177,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_ingest_normals(SpDev d)
     /* S4 (independent of S1): gradient fields, halo 2 */
     for (int e = tid; e < K1_GH * K1_GW; e += K1_THREADS) {
         const int rr = e / K1_GW, cc = e - rr * K1_GW;
-        const int se = (rr + 3) * K1_RW + cc + 3;
-        const float ax = s.sx[se + 1] - s.sx[se - 1], ay = s.sy[se + 1] - s.sy[se - 1], az = s.sz[se + 1] - s.sz[se - 1];
-        const float bx = s.sx[se + K1_RW] - s.sx[se - K1_RW], by = s.sy[se + K1_RW] - s.sy[se - K1_RW], bz = s.sz[se + K1_RW] - s.sz[se - K1_RW];
+        const int se = (rr + 3) * K1_RW + cc + 3, xe = (rr + 1) * K1_XW + cc + 1;
+        const float ax = s.sx[xe + 1] - s.sx[xe - 1], ay = s.sy[xe + 1] - s.sy[xe - 1], az = s.sz[se + 1] - s.sz[se - 1];
+        const float bx = s.sx[xe + K1_XW] - s.sx[xe - K1_XW], by = s.sy[xe + K1_XW] - s.sy[xe - K1_XW], bz = s.sz[se + K1_RW] - s.sz[se - K1_RW];
         const bool fa = sp_finite(ax + (ay + az)), fb = sp_finite(bx + (by + bz));
         s.gx[0][e] = fa ? ax : 0.0f; s.gx[1][e] = fa ? ay : 0.0f; s.gx[2][e] = fa ? az : 0.0f;
         s.gy[0][e] = fb ? bx : 0.0f; s.gy[1][e] = fb ? by : 0.0f; s.gy[2][e] = fb ? bz : 0.0f;
-        s.fx[e] = fa ? 1 : 0; s.fy[e] = fb ? 1 : 0;
+        s.fl[e] = (unsigned char)((fa ? 1 : 0) | (fb ? 2 : 0));
     }
     __syncthreads();
     /* S2: horizontal distance to the nearest flagged pixel, capped at 5 */
@@ -158,118 +200,58 @@ __global__ void __launch_bounds__(K1_THREADS) k_ingest_normals(SpDev d)
     }
     __syncthreads();
 
-    /* S3: smoothing size per owned pixel.  Pixels without a normal (invalid, border, next to a depth discontinuity) are
-     * about a third of the tile: the pixels that do get one are compacted into a list first, so that the box sums below run
-     * with full warps.  kcat[a][h]: rect size implied by a flagged pixel at row distance a, column distance h
-     * (chamfer 1.0/1.4: d = 1.4*min + (max-min); d<=2 -> 0 (NaN), (2,3) -> 2, [3,4) -> 3, [4,5) -> 4, >=5 -> 5) */
-    if (tid == 0) { s.n5 = 0; s.nsmall = 0; }
-    __syncthreads();
+    /* S3: smoothing size per owned pixel.  Pixels without a normal (invalid, border, next to a depth discontinuity: about a
+     * third of the tile) get their NaN here; the others are compacted into one list per window size, so that the box sums
+     * below run with full warps and fixed trip counts.  kcat[a][h]: rect size implied by a flagged pixel at row distance a,
+     * column distance h (chamfer 1.0/1.4: d = 1.4*min + (max-min); d<=2 -> 0 (NaN), (2,3) -> 2, [3,4) -> 3, [4,5) -> 4, >=5 -> 5) */
     const unsigned kcat0 = 0x543000u, kcat1 = 0x543200u, kcat2 = 0x543220u, kcat3 = 0x554333u, kcat4 = 0x555444u;
+    const size_t tile_base = (size_t)f * N + (size_t)r0 * W + c0;
     for (int e = tid; e < K1_TH * K1_TW; e += K1_THREADS) {
         const int rr = e / K1_TW, cc = e - rr * K1_TW;
         const int gr = r0 + rr, gc = c0 + cc;
-        s.onx[e] = qnan; s.ony[e] = qnan; s.onz[e] = qnan;
+        const bool inside = gr < H && gc < W;
         int k = 0;
-        if (gr < H && gc < W && gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO])) {
+        if (inside && gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO])) {
             const unsigned char *col = &s.hd[(rr + 4) * K1_TW + cc];
             k = 5;
             k = min(k, (int)((kcat0 >> (4 * col[0])) & 15u));
-            k = min(k, (int)((kcat1 >> (4 * col[-K1_TW])) & 15u));
-            k = min(k, (int)((kcat1 >> (4 * col[K1_TW])) & 15u));
-            k = min(k, (int)((kcat2 >> (4 * col[-2 * K1_TW])) & 15u));
-            k = min(k, (int)((kcat2 >> (4 * col[2 * K1_TW])) & 15u));
-            k = min(k, (int)((kcat3 >> (4 * col[-3 * K1_TW])) & 15u));
-            k = min(k, (int)((kcat3 >> (4 * col[3 * K1_TW])) & 15u));
-            k = min(k, (int)((kcat4 >> (4 * col[-4 * K1_TW])) & 15u));
-            k = min(k, (int)((kcat4 >> (4 * col[4 * K1_TW])) & 15u));
+            k = min(k, (int)((kcat1 >> (4 * min(col[-K1_TW], col[K1_TW]))) & 15u));
+            k = min(k, (int)((kcat2 >> (4 * min(col[-2 * K1_TW], col[2 * K1_TW]))) & 15u));
+            k = min(k, (int)((kcat3 >> (4 * min(col[-3 * K1_TW], col[3 * K1_TW]))) & 15u));
+            k = min(k, (int)((kcat4 >> (4 * min(col[-4 * K1_TW], col[4 * K1_TW]))) & 15u));
         }
+        if (inside && k < 2) { const size_t gi = tile_base + (size_t)rr * W + cc; d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan; }
         /* warp-aggregated appends: one shared atomic per warp and list */
         const unsigned lanebit = 1u << (tid & 31), lt = lanebit - 1u;
-        const unsigned b5 = __ballot_sync(0xffffffffu, k == 5), bs = __ballot_sync(0xffffffffu, k >= 2 && k < 5);
-        if (b5) {
-            int base = 0;
-            if ((b5 & lt) == 0 && (b5 & lanebit)) base = atomicAdd(&s.n5, __popc(b5));
-            base = __shfl_sync(0xffffffffu, base, __ffs(b5) - 1);
-            if (k == 5) s.list[base + __popc(b5 & lt)] = (unsigned short)e;
-        }
-        if (bs) {
-            int base = 0;
-            if ((bs & lt) == 0 && (bs & lanebit)) base = atomicAdd(&s.nsmall, __popc(bs));
-            base = __shfl_sync(0xffffffffu, base, __ffs(bs) - 1);
-            if (k >= 2 && k < 5) s.list[K1_TH * K1_TW - 1 - (base + __popc(bs & lt))] = (unsigned short)(e | (k << 12));
+#pragma unroll
+        for (int kk = 5; kk >= 3; --kk) {                                  /* kk == 3 stands for the windows of 3 and 2 */
+            const bool mine = kk == 3 ? (k == 3 || k == 2) : k == kk;
+            const unsigned bm = __ballot_sync(0xffffffffu, mine);
+            if (bm) {
+                int *ctr = kk == 5 ? &s.n5 : (kk == 4 ? &s.n4 : &s.n32);
+                int base = 0;
+                if ((bm & lt) == 0 && (bm & lanebit)) base = atomicAdd(ctr, __popc(bm));
+                base = __shfl_sync(0xffffffffu, base, __ffs(bm) - 1);
+                if (mine) {
+                    const int pos = base + __popc(bm & lt);
+                    if (kk == 5) s.list[pos] = (unsigned short)e;
+                    else if (kk == 4) s.list[K1_TH * K1_TW - 1 - pos] = (unsigned short)e;
+                    else if (pos < K1_TH * K1_TW / 2) s.list2[pos] = (unsigned short)(e | (k << 12));
+                    else if (k == 3) k1_normal<3>(s, d, e, tile_base, W);      /* list full (pathological tile): in place */
+                    else k1_normal<2>(s, d, e, tile_base, W);
+                }
+            }
         }
     }
     __syncthreads();
-    /* S5: box sums + normal.  Sum order (the oracle's): rows top to bottom of (row sums left to right), all in double. */
-    auto finish = [&](int e, double sgx0, double sgx1, double sgx2, double sgy0, double sgy1, double sgy2, int cntx, int cnty) {
-        if (cntx != 0 && cnty != 0) {
-            const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
-            const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
-            const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
-            const double L = n0 * n0 + (n1 * n1 + n2 * n2);
-            if (L != 0.0) {
-                const int rr = e / K1_TW, cc = e - rr * K1_TW;
-                const int se = (rr + K1_HALO) * K1_RW + cc + K1_HALO;
-                const float px = s.sx[se], py = s.sy[se], pz = s.sz[se];
-                const double sq = sqrt(L);
-                float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
-                const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
-                const float cs = (vx * fx + vy * fy + vz * fz);
-                if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
-                s.onx[e] = fx; s.ony[e] = fy; s.onz[e] = fz;
-            }
-        }
-    };
-    const int n5 = s.n5, nsmall = s.nsmall;
-    for (int i = tid; i < n5; i += K1_THREADS) {                 /* the 5 x 5 windows: fixed trip counts */
-        const int e = s.list[i];
-        const int rr = e / K1_TW, cc = e - rr * K1_TW;
-        const int g0 = rr * K1_GW + cc;                          /* (rr + 2 - 2, cc + 2 - 2) */
-        double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
-        int cntx = 0, cnty = 0;
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
-            const int gb = g0 + a * K1_GW;
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                const int ge = gb + b;
-                rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
-                ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
-                cntx += s.fx[ge]; cnty += s.fy[ge];
-            }
-            sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
-        }
-        finish(e, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2, cntx, cnty);
-    }
-    for (int i = tid; i < nsmall; i += K1_THREADS) {             /* windows of 2, 3, 4 */
-        const int code = s.list[K1_TH * K1_TW - 1 - i];
-        const int e = code & 0xfff, k = code >> 12;
-        const int rr = e / K1_TW, cc = e - rr * K1_TW;
-        const int half = k >> 1;
-        const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
-        double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
-        int cntx = 0, cnty = 0;
-        for (int a = 0; a < k; ++a) {
-            double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
-            const int gb = g0 + a * K1_GW;
-            for (int b = 0; b < k; ++b) {
-                const int ge = gb + b;
-                rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
-                ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
-                cntx += s.fx[ge]; cnty += s.fy[ge];
-            }
-            sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
-        }
-        finish(e, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2, cntx, cnty);
-    }
-    __syncthreads();
-    for (int e = tid; e < K1_TH * K1_TW; e += K1_THREADS) {
-        const int rr = e / K1_TW, cc = e - rr * K1_TW;
-        const int gr = r0 + rr, gc = c0 + cc;
-        if (gr >= H || gc >= W) continue;
-        const size_t gi = (size_t)f * N + (size_t)gr * W + gc;
-        d.nx[gi] = s.onx[e]; d.ny[gi] = s.ony[e]; d.nz[gi] = s.onz[e];
+    /* S5: box sums + normal, one pass per window size */
+    const int n5 = s.n5, n4 = s.n4, n32 = min(s.n32, K1_TH * K1_TW / 2);
+    for (int i = tid; i < n5; i += K1_THREADS) k1_normal<5>(s, d, s.list[i], tile_base, W);
+    for (int i = tid; i < n4; i += K1_THREADS) k1_normal<4>(s, d, s.list[K1_TH * K1_TW - 1 - i], tile_base, W);
+    for (int i = tid; i < n32; i += K1_THREADS) {
+        const int code = s.list2[i];
+        if ((code >> 12) == 3) k1_normal<3>(s, d, code & 0xfff, tile_base, W);
+        else k1_normal<2>(s, d, code & 0xfff, tile_base, W);
     }
 }
 
