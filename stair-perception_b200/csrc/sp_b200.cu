@@ -203,11 +203,19 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
     if (want_voxel) {
         k_frame_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, nB);
-        mark(ctx, "k_frame_grid");
-        k_voxel_key<<<dim3(std::min(d.nblk, 148), nB), 256, 0, st>>>(d);
+        k_voxel_offsets<<<nB, 256, 0, st>>>(d);
+        k_frame_offsets<<<1, 1024, 0, st>>>(d, nB);
+        mark(ctx, "k_frame_grid+offsets");
+        /* the one host round trip of a chunk: how many cropped points there are to sort */
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, d.foff + nB, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        k_voxel_key<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
         mark(ctx, "k_voxel_key");
-        size_t tb = ctx->cub_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)nB * N, 0, 32 + frame_bits(nB), st));
+        if (total > 0) {
+            size_t tb = ctx->cub_bytes;
+            CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)total, 0, 32 + frame_bits(nB), st));
+        }
         mark(ctx, "radix_sort");
         k_voxel_pick<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
         mark(ctx, "k_voxel_pick");
@@ -215,7 +223,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_scan_blocks");
         k_scatter_lists<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
         mark(ctx, "k_scatter_lists");
-        ctx->launches += 5 + 2 + (32 + frame_bits(nB) + 7) / 8;
+        ctx->launches += 7 + (total > 0 ? 2 + (32 + frame_bits(nB) + 7) / 8 : 0);
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
@@ -332,6 +340,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
     DA(d.x, BN); DA(d.y, BN); DA(d.z, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
+    DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 1);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
     DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
     DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
@@ -615,9 +624,13 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         return SP_OK;
     }
     if (name == "voxel_key") {
-        std::vector<unsigned long long> k(N); CK(d2h(k.data(), d.key_a + f * N, N * 8));
+        std::vector<int> fo(2); CK(d2h(fo.data(), d.foff + f, 8));
+        const size_t M = (size_t)std::max(0, fo[1] - fo[0]);
+        std::vector<unsigned long long> k(M); std::vector<unsigned> v(M);
+        CK(d2h(k.data(), d.key_a + fo[0], M * 8)); CK(d2h(v.data(), d.val_a + fo[0], M * 4));
         out.resize(N * 4); uint32_t *o = (uint32_t *)out.data();
-        for (size_t i = 0; i < N; ++i) o[i] = (uint32_t)k[i];
+        for (size_t i = 0; i < N; ++i) o[i] = 0xFFFFFFFFu;
+        for (size_t i = 0; i < M; ++i) if (v[i] < N) o[v[i]] = (uint32_t)k[i];
         return SP_OK;
     }
     if (name == "voxel_idx" || name == "nonan_idx" || name == "noleg_idx" || name == "voxel_code") {

@@ -79,8 +79,11 @@ struct SpDev {
     int *mm;                   /* [B][8] ordered-int min xyz, max xyz, + 2 pad */
     int *counts;               /* [B][SP_NCOUNT] */
     SpFrameGrid *grid;
+    int *vcnt;                 /* [B][nblk] cropped pixels per 1024-pixel block (K1K2 counts them, the voxel stage compacts by them) */
+    int *voff;                 /* [B][nblk] exclusive scan of vcnt inside the frame */
+    int *foff;                 /* [B + 1] offset of each frame's cropped points in the compacted sort arrays; foff[B'] = total */
     /* voxel */
-    unsigned long long *key_a, *key_b;
+    unsigned long long *key_a, *key_b;   /* only the cropped points are sorted: compacted, frame after frame, pixel order inside */
     unsigned *val_a, *val_b;
     int *rep;                  /* [B][N] */
     unsigned char *code;       /* [B][N] */

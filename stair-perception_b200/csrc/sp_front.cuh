@@ -41,6 +41,7 @@ struct K1Smem {                           /* 54.7 KB: four CTAs per SM */
     unsigned short list[K1_TH * K1_TW];   /* pixels that get a normal, by window size: 5 from the front, 4 from the back */
     unsigned short list2[K1_TH * K1_TW / 2];   /* windows of 3 and 2, tagged (pixel | k << 12); a tile with more takes them in place */
     int n5, n4, n32, pad;
+    int rowcnt[2][K1_TH];                 /* cropped pixels per tile row, split at a 1024-pixel block boundary */
 };
 
 __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
@@ -110,6 +111,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
     }
     const float qnan = __int_as_float(0x7fc00000);
     if (tid == 0) { s.n5 = 0; s.n4 = 0; s.n32 = 0; }
+    if (tid < 2 * K1_TH) (&s.rowcnt[0][0])[tid] = 0;
+    __syncthreads();
 
     /* S0: load tile + halo, level, mask; the owned pixels also go out (levelled xyz) and into the crop statistics */
     {
@@ -146,6 +149,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
                         ++ncrop;
                         mnx = fminf(mnx, ox); mny = fminf(mny, oy); mnz = fminf(mnz, oz);
                         mxx = fmaxf(mxx, ox); mxy = fmaxf(mxy, oy); mxz = fmaxf(mxz, oz);
+                        const int i = gr * W + gc, i0 = gr * W + c0;
+                        atomicAdd(&s.rowcnt[(i >> 10) != (i0 >> 10) ? 1 : 0][tr], 1);
                     }
                 }
             }
@@ -164,6 +169,10 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         if ((tid & 31) == 0 && nvalid) atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
     }
     __syncthreads();
+    if (tid < 2 * K1_TH) {
+        const int tr = tid & (K1_TH - 1), hi = tid >> 5, c = s.rowcnt[hi][tr];
+        if (c) atomicAdd(&d.vcnt[(size_t)f * d.nblk + (((r0 + tr) * W + c0) >> 10) + hi], c);
+    }
 
     /* S1: depth-change flags on the lateral coordinate z (reference quirk), halo 4 */
     for (int e = tid; e < K1_FH * K1_FW; e += K1_THREADS) {
@@ -262,6 +271,7 @@ __global__ void k_init_frames(SpDev d, int nB)
     if (i < nB * SP_NCOUNT) d.counts[i] = 0;
     if (i < nB * 8) { const int k = i & 7; d.mm[i] = (k < 3) ? 0x7fffffff : (int)0x80000000; }
     if (i < nB) d.flags[i] = 0;
+    for (int q = i; q < nB * d.nblk; q += gridDim.x * blockDim.x) d.vcnt[q] = 0;
     if (i < 2 * nB) { d.seg_n[i] = 0; d.n_clusters[i] = 0; d.n_cand[i] = 0; d.log_n[i] = 0; d.n_seg[i] = 0; d.n_merged[i] = 0; }
 }
 
@@ -294,24 +304,86 @@ __global__ void k_frame_grid(SpDev d, int nB)
     d.counts[f * SP_NCOUNT + 0] = g.status;
 }
 
-/* voxel key per point (voxel_grid_indices.hpp:378-394); non-cropped points get the sentinel key */
+/* Only the cropped points go through the sort.  K1K2 left the number of cropped pixels per 1024-pixel block in vcnt; this
+ * kernel turns them into offsets: inside the frame (one CTA per frame) ... */
+__global__ void __launch_bounds__(256) k_voxel_offsets(SpDev d)
+{
+    __shared__ int ws[8];
+    __shared__ int carry;
+    const int f = blockIdx.x, nblk = d.nblk;
+    const bool live = d.grid[f].status == 0;
+    const int *cnt = d.vcnt + (size_t)f * nblk;
+    int *off = d.voff + (size_t)f * nblk;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblk; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        const int v = (live && b < nblk) ? cnt[b] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) ws[wid] = inc;
+        __syncthreads();
+        int add = carry;
+        for (int w = 0; w < wid; ++w) add += ws[w];
+        if (b < nblk) off[b] = add + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = add + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) d.foff[f + 1] = carry;          /* frame total, scanned by k_frame_offsets */
+}
+
+/* ... and across the frames of the chunk (one CTA); foff[nB] = number of elements to sort */
+__global__ void __launch_bounds__(1024) k_frame_offsets(SpDev d, int nB)
+{
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) { carry = 0; d.foff[0] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int f0 = 0; f0 < nB; f0 += 1024) {
+        const int f = f0 + threadIdx.x;
+        const int v = f < nB ? d.foff[f + 1] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) ws[wid] = inc;
+        __syncthreads();
+        int add = carry;
+        for (int w = 0; w < wid; ++w) add += ws[w];
+        __syncthreads();
+        if (f < nB) d.foff[f + 1] = add + inc;
+        if (threadIdx.x == 1023) carry = add + inc;
+        __syncthreads();
+    }
+}
+
+/* voxel key per cropped point (voxel_grid_indices.hpp:378-394), written compacted in pixel order: one CTA per 1024 pixels */
 __global__ void __launch_bounds__(256) k_voxel_key(SpDev d)
 {
+    __shared__ int wsum[33];
     const int f = blockIdx.y, N = d.N;
     const SpFrameGrid g = d.grid[f];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const size_t gi = (size_t)f * N + i;
-        const float px = d.x[gi], py = d.y[gi], pz = d.z[gi];
-        unsigned key = 0xFFFFFFFFu;
-        if (g.status == 0 && sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) &&
-            !(pz < d.c.z0 || pz > d.c.z1)) {
-            const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
-            const int b = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
-            const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
-            key = (unsigned)(a * g.mul[0] + b * g.mul[1] + c * g.mul[2]);
+    if (g.status != 0) return;
+    int pos = d.foff[f] + d.voff[(size_t)f * d.nblk + blockIdx.x];
+    for (int q = 0; q < 4; ++q) {
+        const int i = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+        bool ok = false; unsigned key = 0;
+        if (i < N) {
+            const size_t gi = (size_t)f * N + i;
+            const float px = d.x[gi], py = d.y[gi], pz = d.z[gi];
+            if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
+                const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
+                const int b = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
+                const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
+                key = (unsigned)(a * g.mul[0] + b * g.mul[1] + c * g.mul[2]);
+                ok = true;
+            }
         }
-        d.key_a[gi] = ((unsigned long long)(unsigned)f << 32) | key;
-        d.val_a[gi] = (unsigned)i;
+        int tot;
+        const int r = sp_block_scan_flag(ok, wsum, &tot);
+        if (ok) { d.key_a[pos + r] = ((unsigned long long)(unsigned)f << 32) | key; d.val_a[pos + r] = (unsigned)i; }
+        pos += tot;
     }
 }
 
@@ -326,18 +398,19 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
     const size_t base = (size_t)f * N;
     if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned long long *keys = d.key_b + base;
-    const unsigned *vals = d.val_b + base;
+    const int M = d.foff[f + 1] - d.foff[f];                       /* this frame's cropped points, sorted by voxel */
+    const unsigned long long *keys = d.key_b + d.foff[f];
+    const unsigned *vals = d.val_b + d.foff[f];
     const float *X = d.x + base, *Y = d.y + base, *Z = d.z + base;
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     for (int q = 0; q < 4; ++q) {
         const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
         if (j >= N) break;
-        const unsigned long long key = keys[j];
         unsigned char code = 0; int rep = -1;
-        if ((unsigned)key != 0xFFFFFFFFu && (j == 0 || keys[j - 1] != key)) {
+        const unsigned long long key = j < M ? keys[j] : 0ull;
+        if (j < M && (j == 0 || keys[j - 1] != key)) {
             float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-            for (int t = j; t < N && keys[t] == key; ++t) { const unsigned p = vals[t]; sx += X[p]; sy += Y[p]; sz += Z[p]; ++n; }
+            for (int t = j; t < M && keys[t] == key; ++t) { const unsigned p = vals[t]; sx += X[p]; sy += Y[p]; sz += Z[p]; ++n; }
             const float fn = (float)n;
             const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
             float best = FLT_MAX;

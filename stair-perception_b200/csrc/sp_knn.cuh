@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) k_ingest_plain(SpDev d, int *knn_mm)
         const size_t gi = (size_t)f * N + i;
         d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz;
         d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan;
+        bool crop = false;
         if (sp_finite3(ox, oy, oz)) {
             ++nvalid;
             const int o0 = sp_f2ord(ox), o1 = sp_f2ord(oy), o2 = sp_f2ord(oz);
@@ -60,9 +61,15 @@ __global__ void __launch_bounds__(256) k_ingest_plain(SpDev d, int *knn_mm)
             ax[0] = max(ax[0], o0); ax[1] = max(ax[1], o1); ax[2] = max(ax[2], o2);
             if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {
                 ++ncrop;
+                crop = true;
                 mn[0] = min(mn[0], o0); mn[1] = min(mn[1], o1); mn[2] = min(mn[2], o2);
                 mx[0] = max(mx[0], o0); mx[1] = max(mx[1], o1); mx[2] = max(mx[2], o2);
             }
+        }
+        {   /* cropped points per 1024-point block (the voxel stage compacts by them): a warp's 32 points share a block */
+            const unsigned am = __activemask();
+            const unsigned bm = __ballot_sync(am, crop);
+            if (bm && (threadIdx.x & 31) == __ffs(am) - 1) atomicAdd(&d.vcnt[(size_t)f * d.nblk + (i >> 10)], __popc(bm));
         }
     }
 #pragma unroll
