@@ -108,7 +108,8 @@ struct sp_ctx {
     void *cub_temp = nullptr; size_t cub_bytes = 0;
     float4 *d_in[2] = { nullptr, nullptr }; float *d_R[2] = { nullptr, nullptr };
     int *d_order = nullptr;
-    sp_frame_result *h_results = nullptr;     /* pinned */
+    sp_frame_result *h_results = nullptr;     /* pinned, two chunks: the host copies chunk i out while chunk i+1 runs */
+    cudaEvent_t ev_res[2] = { nullptr, nullptr };
     cudaEvent_t ev[STG_COUNT + 1];
     cudaEvent_t ev_in[2], ev_done[2];
     float stage_ms[STG_COUNT];
@@ -374,7 +375,8 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
         if ((e = cudaMalloc(&q, std::max<size_t>(tb, 16))) != cudaSuccess) return fail("cudaMalloc cub", e);
         ctx->allocs.push_back(q); ctx->cub_temp = q;
     }
-    if ((e = cudaMallocHost((void **)&ctx->h_results, sizeof(sp_frame_result) * B)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void **)&ctx->h_results, sizeof(sp_frame_result) * B * 2)) != cudaSuccess) return fail("cudaMallocHost", e);
+    for (int i = 0; i < 2; ++i) if ((e = cudaEventCreateWithFlags(&ctx->ev_res[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
     *out = ctx;
@@ -391,6 +393,7 @@ void sp_destroy(sp_ctx *ctx)
     for (int i = 0; i <= STG_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
     for (cudaEvent_t e : ctx->tev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_res[i]) cudaEventDestroy(ctx->ev_res[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -458,10 +461,20 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         const int rc = run_chunk(ctx, din, dR, nB, show_mode, -1);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_results, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        memcpy(results + f0, ctx->h_results, sizeof(sp_frame_result) * nB);
+        /* results travel one chunk behind: chunk ci is copied out of its pinned buffer while chunk ci + 1 runs */
+        CK(cudaMemcpyAsync(ctx->h_results + (size_t)(ci & 1) * ctx->B, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_res[ci & 1], ctx->stream));
+        if (ci > 0) {
+            const int pf0 = (ci - 1) * ctx->B, pn = std::min(ctx->B, nframes - pf0);
+            CK(cudaEventSynchronize(ctx->ev_res[(ci - 1) & 1]));
+            memcpy(results + pf0, ctx->h_results + (size_t)((ci - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
+        }
         buf ^= 1;
+    }
+    if (nchunks > 0) {
+        const int pf0 = (nchunks - 1) * ctx->B, pn = nframes - pf0;
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(results + pf0, ctx->h_results + (size_t)((nchunks - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
     }
     collect_times(ctx);
     return SP_OK;
@@ -518,10 +531,20 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         const int rc = run_chunk(ctx, ctx->d_in[buf], R9 ? ctx->d_R[buf] : nullptr, nB, show_mode, -1);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_results, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        memcpy(results + f0, ctx->h_results, sizeof(sp_frame_result) * nB);
+        /* results travel one chunk behind: chunk ci is copied out of its pinned buffer while chunk ci + 1 runs */
+        CK(cudaMemcpyAsync(ctx->h_results + (size_t)(ci & 1) * ctx->B, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_res[ci & 1], ctx->stream));
+        if (ci > 0) {
+            const int pf0 = (ci - 1) * ctx->B, pn = std::min(ctx->B, nframes - pf0);
+            CK(cudaEventSynchronize(ctx->ev_res[(ci - 1) & 1]));
+            memcpy(results + pf0, ctx->h_results + (size_t)((ci - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
+        }
         buf ^= 1;
+    }
+    if (nchunks > 0) {
+        const int pf0 = (nchunks - 1) * ctx->B, pn = nframes - pf0;
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(results + pf0, ctx->h_results + (size_t)((nchunks - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
     }
     collect_times(ctx);
     return SP_OK;
