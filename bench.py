@@ -36,6 +36,36 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and so its first-touch pinned host buffers) to the CPUs of the GPU's NUMA node: with one rank per GPU
+    the H2D copies of the end-to-end leg then read local memory.  Best effort; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                       # nvml pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def load_traffic(kernel, frames_per_launch):
     """dram bytes of one launch from the committed ncu capture (profiles/r01_traffic.json), or None"""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -185,6 +215,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -320,7 +351,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config 5: batch of synthetic Kinect-V2 4-step stair frames, 512x424 (217088 pts), levelling + full segmentation front-end",
                        "frames_per_gpu_per_step": F, "distinct_frames": N_DISTINCT, "max_batch": args.max_batch,
-                       "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (F * N * 16 / 1e9), "parallelism": "frames sharded across %d GPU(s)" % world},
+                       "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (F * N * 16 / 1e9), "parallelism": "frames sharded across %d GPU(s)" % world,
+                       "host_numa_binding": numa_node},
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 16 + 36)),
                     "d2h_bytes_per_step": int(Fe * sp.FRAME_DTYPE.itemsize), "frames_per_gpu_per_step": Fe, "ms_per_step": ms_e / args.steps},
             "e2e_depth_input": {"value": depth_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 6 + 36)),
