@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
 
 /* sortPlanesByXValues (StairPerception.cpp:1383-1441) + the per-frame result record; one thread per frame.
  * order[f][i] = (segment-local merged plane index) | hv << 16 is kept for the plane point gather. */
-__global__ void k_finalize(SpDev d, int nB, int *order, int with_planes)
+__global__ void k_finalize(SpDev d, int nB, int *order, int with_planes, int show_mode)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nB) return;
@@ -924,6 +924,15 @@ __global__ void k_finalize(SpDev d, int nB, int *order, int with_planes)
     R.n_seg_h = d.n_seg[2 * f]; R.n_seg_v = d.n_seg[2 * f + 1];
     int nh = d.n_merged[2 * f], nv = d.n_merged[2 * f + 1];
     R.n_planes_h = nh; R.n_planes_v = nv;
+    /* process() returns at the ShowModeDef tap (StairPerception.cpp:49-176): nothing computed past it is reported, even
+     * where a fused kernel happened to produce it (H and V sets are classified, clustered and segmented together) */
+    if (show_mode < SP_SHOW_VOXEL) { R.n_voxel = 0; R.n_nonan = 0; }
+    if (show_mode < SP_SHOW_NOLEG) R.n_noleg = 0;
+    if (show_mode < SP_SHOW_HORIZONTAL_CLOUD) { R.n_h = 0; R.n_v = 0; }
+    if (show_mode < SP_SHOW_SEG_HORIZONTAL_PLANE) { R.n_clusters_h = 0; R.n_seg_h = 0; }
+    if (show_mode < SP_SHOW_SEG_VERTICAL_PLANE) { R.n_clusters_v = 0; R.n_seg_v = 0; }
+    if (show_mode < SP_SHOW_MERGE_HORIZONTAL_PLANE) R.n_planes_h = 0;
+    if (show_mode < SP_SHOW_MERGE_VERTICAL_PLANE) R.n_planes_v = 0;
     if (!with_planes) { nh = 0; nv = 0; }
     float chx[SP_PSEG], cvx[SP_PSEG];
     for (int i = 0; i < nh; ++i) chx[i] = d.info[(2 * f) * SP_PSEG + i].center[0];

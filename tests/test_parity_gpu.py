@@ -312,3 +312,16 @@ def test_other_image_sizes(sp, orc, samples, w, h):
         bad = compare_frame(ctx, f, res[f], o)
         assert not bad, "\n".join(bad[:20])
     ctx.close()
+
+
+def test_fuzzed_parameters_and_scenes(sp):
+    """random ParameterDef values inside the GUI's ranges, random staircases and dropout, random show modes, with and
+    without levelling: every count and every tap equals the oracle's (tools/fuzz_parity.py; 480 more cases were run in round 1)"""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tools", "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    fails = fz.run(16, 2026, verbose=False)
+    assert not fails, fails[:2]
