@@ -325,3 +325,25 @@ def test_fuzzed_parameters_and_scenes(sp):
     spec.loader.exec_module(fz)
     fails = fz.run(16, 2026, verbose=False)
     assert not fails, fails[:2]
+
+
+def test_mixed_batch_with_empty_and_sparse_frames(sp, orc, synth):
+    """one chunk holding ordinary frames next to an empty one (status 1: fewer than 100 points after the crop) and a sparse
+    one: the compacted voxel sort and every per-frame offset must keep the frames apart"""
+    frames = []
+    for fid in (31, 32, 33, 34, 35):
+        rec, R = synth.make_frame(fid)
+        frames.append([rec.copy(), R])
+    frames[1][0]["rgba"] = 0                                              # empty
+    keep = np.zeros((424, 512), dtype=bool)
+    keep[100:130, 200:260] = True
+    frames[3][0]["rgba"] = np.where(keep.reshape(-1), frames[3][0]["rgba"], 0)   # 1 800 pixels at most
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=5)
+    res = ctx.process_frames(np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]))
+    assert int(res[1]["status"]) == 1 and int(res[1]["n_planes"]) == 0
+    for f in range(5):
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(frames[f][0], 512, 424, frames[f][1])
+        bad = compare_frame(ctx, f, res[f], o)
+        assert not bad, "frame %d\n" % f + "\n".join(bad[:20])
+    ctx.close()
