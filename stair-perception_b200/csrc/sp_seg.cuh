@@ -343,7 +343,7 @@ __device__ __forceinline__ bool rs_model_valid(const SpConst &c, bool parallel, 
     return !((double)fabsf(c0) > c.sin_angle);
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_ransac(SpDev d)
+__global__ void __launch_bounds__(RS_THREADS, 4) k_ransac(SpDev d)
 {
     __shared__ RsSmem S;
     const int s = blockIdx.y, ci = blockIdx.x;
