@@ -188,7 +188,7 @@ struct KnnWarp {
     float accu[9];
 };
 
-__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_normals(SpDev d, const SpKnnGrid *grid, const int *bstart, const int *bend,
+__global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, const SpKnnGrid *grid, const int *bstart, const int *bend,
                                                                 const float4 *kpts, int k)
 {
     __shared__ KnnWarp S[KNN_WARPS];
