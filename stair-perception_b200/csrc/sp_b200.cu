@@ -187,18 +187,19 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         k_ingest_plain<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_mm);
         mark(ctx, "k_ingest_plain");
         k_knn_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, ctx->knn_mm, ctx->knn_grid, k, nB);
-        k_knn_key<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_grid);
-        mark(ctx, "k_knn_key");
-        size_t tb = ctx->cub_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)nB * N, 0, 32 + frame_bits(nB), st));
-        mark(ctx, "knn_radix_sort");
-        CK(cudaMemsetAsync(ctx->knn_bstart, 0, sizeof(int) * ((size_t)nB << KNN_BITS), st));
-        CK(cudaMemsetAsync(ctx->knn_bend, 0, sizeof(int) * ((size_t)nB << KNN_BITS), st));
-        k_knn_starts<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_bstart, ctx->knn_bend, ctx->knn_pts);
-        mark(ctx, "k_knn_starts");
+        for (int pass = 0; pass < 2; ++pass) {                 /* pass 0 probes the surface density, pass 1 uses the refined cell edge */
+            if (pass == 1) k_knn_refine<<<(nB + 127) / 128, 128, 0, st>>>(ctx->knn_grid, k, nB);
+            k_knn_key<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_grid);
+            size_t tb = ctx->cub_bytes;
+            CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)nB * N, 0, 32 + frame_bits(nB), st));
+            CK(cudaMemsetAsync(ctx->knn_bstart, 0, sizeof(int) * ((size_t)nB << KNN_BITS), st));
+            CK(cudaMemsetAsync(ctx->knn_bend, 0, sizeof(int) * ((size_t)nB << KNN_BITS), st));
+            k_knn_starts<<<dim3(gx, nB), 256, 0, st>>>(d, ctx->knn_bstart, ctx->knn_bend, ctx->knn_pts, ctx->knn_grid);
+        }
+        mark(ctx, "knn_grid_build(2x)");
         k_knn_normals<<<dim3(148 * 8, nB), KNN_WARPS * 32, 0, st>>>(d, ctx->knn_grid, ctx->knn_bstart, ctx->knn_bend, ctx->knn_pts, k);
         mark(ctx, "k_knn_normals");
-        ctx->launches += 7 + 2 + (32 + frame_bits(nB) + 7) / 8;
+        ctx->launches += 6 + 2 * (2 + 2 + (32 + frame_bits(nB) + 7) / 8);
     }
     CK(cudaEventRecord(ctx->ev[1], st));
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;

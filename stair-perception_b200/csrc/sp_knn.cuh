@@ -20,7 +20,7 @@
 #define KNN_WARPS 8
 #define KNN_MAX_SHELL 12
 
-struct SpKnnGrid { float h; int nvalid; int pad0, pad1; };
+struct SpKnnGrid { float h; int nvalid; int occupied; int pad1; };   /* occupied = hashed cells that hold points (density probe) */
 
 /* levelling + masking + crop predicate / bounding box / counts (what k_ingest_normals does besides the normals) for a
  * cloud without image structure; also the bounding box of ALL finite points (kNN search surface) */
@@ -101,7 +101,7 @@ __global__ void k_knn_grid(SpDev d, const int *knn_mm, SpKnnGrid *grid, int k, i
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nB) return;
-    SpKnnGrid g; g.pad0 = g.pad1 = 0;
+    SpKnnGrid g; g.occupied = 0; g.pad1 = 0;
     g.nvalid = d.counts[f * SP_NCOUNT + 1];
     g.h = 1.0f;
     if (g.nvalid > 0) {
@@ -111,6 +111,23 @@ __global__ void k_knn_grid(SpDev d, const int *knn_mm, SpKnnGrid *grid, int k, i
         float h = sqrtf(fmaxf(1e-12f, area * (float)k / (3.14159265f * (float)g.nvalid)));
         g.h = fminf(fmaxf(h, 1e-4f), 1e6f);
     }
+    grid[f] = g;
+}
+
+/* second look at the cell edge: the first grid told how many points share an occupied cell (m = surface density x h^2), and
+ * k neighbours need pi h^2 density >= k, so h <- h sqrt(k / (pi m)).  The bounding-box guess above can be off by 2x on scenes
+ * that are mostly empty space, which quadruples the candidates every query has to rank. */
+__global__ void k_knn_refine(SpKnnGrid *grid, int k, int nB)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nB) return;
+    SpKnnGrid g = grid[f];
+    if (g.nvalid > 0 && g.occupied > 0) {
+        const float m = (float)g.nvalid / (float)g.occupied;
+        const float h = g.h * sqrtf((float)k / (3.14159265f * m)) * 1.05f;
+        g.h = fminf(fmaxf(h, 1e-4f), 1e6f);
+    }
+    g.occupied = 0;
     grid[f] = g;
 }
 
@@ -135,7 +152,7 @@ __global__ void __launch_bounds__(256) k_knn_key(SpDev d, const SpKnnGrid *grid)
 }
 
 /* after the sort: bucket ranges + the points in bucket order {x, y, z, point index} */
-__global__ void __launch_bounds__(256) k_knn_starts(SpDev d, int *bstart, int *bend, float4 *kpts)
+__global__ void __launch_bounds__(256) k_knn_starts(SpDev d, int *bstart, int *bend, float4 *kpts, SpKnnGrid *grid)
 {
     const int f = blockIdx.y, N = d.N;
     const size_t base = (size_t)f * N;
@@ -145,7 +162,7 @@ __global__ void __launch_bounds__(256) k_knn_starts(SpDev d, int *bstart, int *b
         if (key == 0xFFFFFFFFu) continue;
         const unsigned pix = d.val_b[base + j];
         kpts[base + j] = make_float4(d.x[base + pix], d.y[base + pix], d.z[base + pix], __int_as_float((int)pix));
-        if (j == 0 || (unsigned)d.key_b[base + j - 1] != key) bs[key] = j;
+        if (j == 0 || (unsigned)d.key_b[base + j - 1] != key) { bs[key] = j; atomicAdd(&grid[f].occupied, 1); }
         if (j == N - 1 || (unsigned)d.key_b[base + j + 1] != key) be[key] = j + 1;
     }
 }
