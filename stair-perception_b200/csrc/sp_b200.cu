@@ -116,6 +116,8 @@ struct sp_ctx {
     /* per-kernel trace of the last chunk (SP_TRACE=1 or sp_set_trace): one event after every launch */
     /* a3' kNN normals (unorganised clouds): allocated on first use */
     int normal_mode = 0;
+    std::vector<int> h_foff;                  /* host copy of foff (one read per chunk) */
+    bool force_key64 = false;                 /* SP_KEY64=1: always the 64-bit voxel sort (parity tests of that path) */
     int *knn_mm = nullptr, *knn_bstart = nullptr, *knn_bend = nullptr;
     SpKnnGrid *knn_grid = nullptr;
     float4 *knn_pts = nullptr;
@@ -208,15 +210,41 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         k_voxel_offsets<<<nB, 256, 0, st>>>(d);
         k_frame_offsets<<<1, 1024, 0, st>>>(d, nB);
         mark(ctx, "k_frame_grid+offsets");
-        /* the one host round trip of a chunk: how many cropped points there are to sort */
-        int total = 0;
-        CK(cudaMemcpyAsync(&total, d.foff + nB, sizeof(int), cudaMemcpyDeviceToHost, st));
+        /* the one host round trip of a chunk: where each frame's cropped points sit in the sort arrays, and how many bits the
+         * largest voxel grid of the chunk needs */
+        std::vector<int> &fo = ctx->h_foff;
+        fo.resize((size_t)nB + 2);
+        CK(cudaMemcpyAsync(fo.data(), d.foff, sizeof(int) * ((size_t)nB + 2), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const int total = fo[nB];
+        int vbits = 1;                                                       /* 0x7fffffff = some frame's indices wrapped: 32 bits */
+        while (vbits < 32 && (fo[nB + 1] == 0x7fffffff || (1LL << vbits) < (long long)fo[nB + 1])) ++vbits;
+        const int room = 1 << std::min(30, 32 - vbits);                      /* frames that fit beside the voxel bits in 32 bits */
+        d.key32 = (room >= 32 || room >= nB) ? 1 : 0;
+        if (ctx->force_key64) d.key32 = 0;
+        d.vbits = vbits;
+        d.fgroup = 1;
+        while (d.fgroup < nB && d.fgroup < room) d.fgroup <<= 1;
+        ctx->d.key32 = d.key32; ctx->d.vbits = d.vbits; ctx->d.fgroup = d.fgroup;
         k_voxel_key<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
         mark(ctx, "k_voxel_key");
-        if (total > 0) {
+        int nsort = 0;
+        if (total > 0 && d.key32) {
+            /* stable LSD sort of (frame-in-group, voxel index) keys: ceil((vbits + log2 fgroup) / 8) passes of 8 B per point */
+            int gbits = 0;
+            while ((1 << gbits) < d.fgroup) ++gbits;
+            for (int g0 = 0; g0 < nB; g0 += d.fgroup) {
+                const int o0 = fo[g0], o1 = fo[std::min(nB, g0 + d.fgroup)];
+                if (o1 <= o0) continue;
+                size_t tb = ctx->cub_bytes;
+                CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, reinterpret_cast<unsigned *>(d.key_a) + o0, reinterpret_cast<unsigned *>(d.key_b) + o0,
+                                                   d.val_a + o0, d.val_b + o0, (size_t)(o1 - o0), 0, std::min(32, vbits + gbits), st));
+                nsort += 2 + (std::min(32, vbits + gbits) + 7) / 8;
+            }
+        } else if (total > 0) {
             size_t tb = ctx->cub_bytes;
             CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)total, 0, 32 + frame_bits(nB), st));
+            nsort = 2 + (32 + frame_bits(nB) + 7) / 8;
         }
         mark(ctx, "radix_sort");
         k_voxel_pick<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
@@ -225,7 +253,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_scan_blocks");
         k_scatter_lists<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
         mark(ctx, "k_scatter_lists");
-        ctx->launches += 7 + (total > 0 ? 2 + (32 + frame_bits(nB) + 7) / 8 : 0);
+        ctx->launches += 7 + nsort;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
@@ -318,6 +346,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     sp_ctx *ctx = new sp_ctx();
     ctx->device = device; ctx->W = width; ctx->H = height; ctx->N = width * height; ctx->B = max_batch;
     { const char *t = getenv("SP_TRACE"); ctx->trace = t && *t && *t != '0'; }
+    { const char *t = getenv("SP_KEY64"); ctx->force_key64 = t && *t && *t != '0'; }
     memset(&ctx->d, 0, sizeof(ctx->d));
     memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
     auto fail = [&](const char *what, cudaError_t err) {
@@ -342,7 +371,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
     DA(d.x, BN); DA(d.y, BN); DA(d.z, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
-    DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 1);
+    DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 2);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
     DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
     DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
@@ -651,7 +680,12 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         std::vector<int> fo(2); CK(d2h(fo.data(), d.foff + f, 8));
         const size_t M = (size_t)std::max(0, fo[1] - fo[0]);
         std::vector<unsigned long long> k(M); std::vector<unsigned> v(M);
-        CK(d2h(k.data(), d.key_a + fo[0], M * 8)); CK(d2h(v.data(), d.val_a + fo[0], M * 4));
+        if (d.key32) {
+            std::vector<unsigned> k4(M);
+            CK(d2h(k4.data(), reinterpret_cast<unsigned *>(d.key_a) + fo[0], M * 4));
+            for (size_t i = 0; i < M; ++i) k[i] = k4[i] & (unsigned)((1ull << d.vbits) - 1ull);   /* vbits <= 32 */
+        } else CK(d2h(k.data(), d.key_a + fo[0], M * 8));
+        CK(d2h(v.data(), d.val_a + fo[0], M * 4));
         out.resize(N * 4); uint32_t *o = (uint32_t *)out.data();
         for (size_t i = 0; i < N; ++i) o[i] = 0xFFFFFFFFu;
         for (size_t i = 0; i < M; ++i) if (v[i] < N) o[v[i]] = (uint32_t)k[i];

@@ -282,7 +282,7 @@ __global__ void k_frame_grid(SpDev d, int nB)
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nB) return;
     SpFrameGrid g;
-    g.status = 0; g.pad = 0;
+    g.status = 0; g.cells = 0;
     const int ncrop = d.counts[f * SP_NCOUNT + 2];
     for (int k = 0; k < 3; ++k) { g.minb[k] = 0; g.mul[k] = 0; }
     if (ncrop < 100) g.status = 1;
@@ -298,6 +298,11 @@ __global__ void k_frame_grid(SpDev d, int nB)
             const int m0 = (int)floorf(mxx * d.c.ivx), m1 = (int)floorf(mxy * d.c.ivy);
             const int d0 = m0 - g.minb[0] + 1, d1 = m1 - g.minb[1] + 1;
             g.mul[0] = 1; g.mul[1] = d0; g.mul[2] = d0 * d1;
+            /* bound of the voxel indices k_voxel_key forms (floor differences, one more than dx, dy, dz at most); a product past
+             * int range means wrapped indices that need all 32 bits */
+            const long long d2 = (long long)((int)floorf(mxz * d.c.ivz) - g.minb[2] + 1);
+            const long long cells = (long long)d0 * d1 * d2;
+            g.cells = cells > 2147483647LL ? -1 : (int)cells;
         }
     }
     d.grid[f] = g;
@@ -338,13 +343,14 @@ __global__ void __launch_bounds__(256) k_voxel_offsets(SpDev d)
 __global__ void __launch_bounds__(1024) k_frame_offsets(SpDev d, int nB)
 {
     __shared__ int ws[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) { carry = 0; d.foff[0] = 0; }
+    __shared__ int carry, cmax;
+    if (threadIdx.x == 0) { carry = 0; cmax = 0; d.foff[0] = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int f0 = 0; f0 < nB; f0 += 1024) {
         const int f = f0 + threadIdx.x;
         const int v = f < nB ? d.foff[f + 1] : 0;
+        if (f < nB) { const int c = d.grid[f].cells; atomicMax(&cmax, c < 0 ? 0x7fffffff : c); }
         int inc = v;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) ws[wid] = inc;
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(1024) k_frame_offsets(SpDev d, int nB)
         if (threadIdx.x == 1023) carry = add + inc;
         __syncthreads();
     }
+    if (threadIdx.x == 0) d.foff[nB + 1] = cmax;
 }
 
 /* voxel key per cropped point (voxel_grid_indices.hpp:378-394), written compacted in pixel order: one CTA per 1024 pixels */
@@ -382,7 +389,11 @@ __global__ void __launch_bounds__(256) k_voxel_key(SpDev d)
         }
         int tot;
         const int r = sp_block_scan_flag(ok, wsum, &tot);
-        if (ok) { d.key_a[pos + r] = ((unsigned long long)(unsigned)f << 32) | key; d.val_a[pos + r] = (unsigned)i; }
+        if (ok) {
+            if (d.key32) reinterpret_cast<unsigned *>(d.key_a)[pos + r] = (d.fgroup > 1 ? ((unsigned)(f & (d.fgroup - 1)) << d.vbits) : 0u) | key;
+            else d.key_a[pos + r] = ((unsigned long long)(unsigned)f << 32) | key;
+            d.val_a[pos + r] = (unsigned)i;
+        }
         pos += tot;
     }
 }
@@ -399,7 +410,10 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
     if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
     __syncthreads();
     const int M = d.foff[f + 1] - d.foff[f];                       /* this frame's cropped points, sorted by voxel */
-    const unsigned long long *keys = d.key_b + d.foff[f];
+    const bool k32 = d.key32 != 0;
+    const unsigned long long *keys64 = d.key_b + d.foff[f];
+    const unsigned *keys32 = reinterpret_cast<const unsigned *>(d.key_b) + d.foff[f];
+    auto key_at = [&](int t) -> unsigned long long { return k32 ? (unsigned long long)keys32[t] : keys64[t]; };
     const unsigned *vals = d.val_b + d.foff[f];
     const float *X = d.x + base, *Y = d.y + base, *Z = d.z + base;
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
@@ -407,10 +421,10 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
         const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
         if (j >= N) break;
         unsigned char code = 0; int rep = -1;
-        const unsigned long long key = j < M ? keys[j] : 0ull;
-        if (j < M && (j == 0 || keys[j - 1] != key)) {
+        const unsigned long long key = j < M ? key_at(j) : 0ull;
+        if (j < M && (j == 0 || key_at(j - 1) != key)) {
             float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-            for (int t = j; t < M && keys[t] == key; ++t) { const unsigned p = vals[t]; sx += X[p]; sy += Y[p]; sz += Z[p]; ++n; }
+            for (int t = j; t < M && key_at(t) == key; ++t) { const unsigned p = vals[t]; sx += X[p]; sy += Y[p]; sz += Z[p]; ++n; }
             const float fn = (float)n;
             const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
             float best = FLT_MAX;
