@@ -31,18 +31,21 @@
 #define K1_GH (K1_TH + 4)
 #define K1_THREADS 256
 
-struct K1Smem {                           /* 54.7 KB: four CTAs per SM */
+struct K1Smem {                           /* 55.6 KB: four CTAs per SM */
     float sz[K1_RH * K1_RW];
     float sx[K1_XH * K1_XW], sy[K1_XH * K1_XW];
     float gx[3][K1_GH * K1_GW], gy[3][K1_GH * K1_GW];
-    unsigned char zero[K1_FH * K1_FW];
-    unsigned char hd[K1_FH * K1_TW];
+    unsigned long long dil[5][K1_FH];     /* bit rows of the flag region (bit c = column c): depth-change pixels dilated by 0..4 columns */
+    unsigned zlo[K1_FH], zhi[K1_FH];      /* the undilated rows as the ballots deliver them: columns 0..31 and 32..39 */
+    unsigned kmask[4][K1_TH];             /* per tile row: pixels whose smoothing window is 5, 4, 3, 2 */
+    unsigned vmask[K1_TH], imask[K1_TH];  /* pixels that may get a normal (image border, finite z); pixels inside the image */
+    unsigned short base[3][K1_TH];        /* where a row's window-5 / window-4 / window-3-and-2 pixels start in their list */
     unsigned char fl[K1_GH * K1_GW];      /* finite flags of the gradient elements: bit 0 = dx, bit 1 = dy */
     unsigned short list[K1_TH * K1_TW];   /* pixels that get a normal, by window size: 5 from the front, 4 from the back */
     unsigned short list2[K1_TH * K1_TW / 2];   /* windows of 3 and 2, tagged (pixel | k << 12); a tile with more takes them in place */
     int n5, n4, n32, pad;
-    int rowcnt[2][K1_TH];                 /* cropped pixels per tile row, split at a 1024-pixel block boundary */
 };
+static_assert(K1_FW <= 64 && K1_TW == 32, "bit rows: one 64-bit word per flag row, one warp lane per tile column");
 
 __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
 {
@@ -101,29 +104,25 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
     K1Smem &s = *reinterpret_cast<K1Smem *>(k1_raw);
     const int f = blockIdx.z, W = d.W, H = d.H, N = d.N;
     const int r0 = blockIdx.y * K1_TH, c0 = blockIdx.x * K1_TW;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
     const float4 *in = d.in + (size_t)f * N;
-    float R[9];
-    const bool rot = d.R != nullptr;
-    if (rot) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = __ldg(d.R + 9 * f + i);
-    }
     const float qnan = __int_as_float(0x7fc00000);
-    if (tid == 0) { s.n5 = 0; s.n4 = 0; s.n32 = 0; }
-    if (tid < 2 * K1_TH) (&s.rowcnt[0][0])[tid] = 0;
-    __syncthreads();
+    const size_t tile_base = (size_t)f * N + (size_t)r0 * W + c0;
 
-    /* S0: load tile + halo, level, mask; the owned pixels also go out (levelled xyz) and into the crop statistics */
+    /* S0: load tile + halo, level, mask -> shared memory (flat index, row / column kept incrementally: 256 = 6 * 42 + 4) */
     {
-        float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
-        int nvalid = 0, ncrop = 0;
+        float R[9];
+        const bool rot = d.R != nullptr;
+        if (rot) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = __ldg(d.R + 9 * f + i);
+        }
+        int rr = tid / K1_RW, cc = tid - rr * K1_RW;
         for (int e = tid; e < K1_RH * K1_RW; e += K1_THREADS) {
-            const int rr = e / K1_RW, cc = e - rr * K1_RW;
             const int gr = r0 - K1_HALO + rr, gc = c0 - K1_HALO + cc;
             float ox = qnan, oy = qnan, oz = qnan;
-            const bool inside = gr >= 0 && gr < H && gc >= 0 && gc < W;
-            if (inside) {
+            if (gr >= 0 && gr < H && gc >= 0 && gc < W) {
                 const float4 p = __ldg(in + (size_t)gr * W + gc);
                 ox = p.x; oy = p.y; oz = p.z;
                 if (rot) {
@@ -133,123 +132,153 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
                         oz = R[6] * p.x + R[7] * p.y + R[8] * p.z;
                     } else { ox = oy = oz = qnan; }
                 }
-                const unsigned rgba = __float_as_uint(p.w);
-                if ((rgba & 255u) == 0u || ((rgba >> 8) & 255u) == 0u || ((rgba >> 16) & 255u) == 0u) { ox = oy = oz = qnan; }
+                /* remove_nan_points: r, g or b == 0 marks an invalid pixel (per-byte compare of the three colour bytes) */
+                if (__vcmpeq4(__float_as_uint(p.w) | 0xff000000u, 0u)) { ox = oy = oz = qnan; }
             }
             s.sz[e] = oz;
-            const int xr = rr - 2, xc = cc - 2;                                  /* x, y keep a halo of 3 */
-            if (xr >= 0 && xr < K1_XH && xc >= 0 && xc < K1_XW) { s.sx[xr * K1_XW + xc] = ox; s.sy[xr * K1_XW + xc] = oy; }
-            const int tr = rr - K1_HALO, tc = cc - K1_HALO;
-            if (inside && tr >= 0 && tr < K1_TH && tc >= 0 && tc < K1_TW) {       /* owned pixel */
-                const size_t gi = (size_t)f * N + (size_t)gr * W + gc;
+            const unsigned xr = (unsigned)(rr - 2), xc = (unsigned)(cc - 2);       /* x, y keep a halo of 3 */
+            if (xr < (unsigned)K1_XH && xc < (unsigned)K1_XW) { s.sx[xr * K1_XW + xc] = ox; s.sy[xr * K1_XW + xc] = oy; }
+            cc += K1_THREADS % K1_RW; rr += K1_THREADS / K1_RW;
+            if (cc >= K1_RW) { cc -= K1_RW; ++rr; }
+        }
+    }
+    __syncthreads();
+
+    /* S0b: the owned pixels, one warp per tile row (lane = column): levelled xyz out, crop statistics of
+     * passThroughCloudANDNormal / getMinMax3D, cropped pixels per 1024-pixel block for the voxel stage, row masks */
+    {
+        float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
+        int nvalid = 0, ncrop = 0;
+        const int gc = c0 + lane;
+#pragma unroll
+        for (int it = 0; it < K1_TH / 8; ++it) {
+            const int tr = it * 8 + wid, gr = r0 + tr;
+            const int xe = (tr + 3) * K1_XW + lane + 3;
+            const float ox = s.sx[xe], oy = s.sy[xe], oz = s.sz[(tr + K1_HALO) * K1_RW + lane + K1_HALO];
+            const bool inside = gr < H && gc < W;
+            bool crop = false;
+            if (inside) {
+                const size_t gi = tile_base + (size_t)tr * W + lane;
                 d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz;
                 if (sp_finite3(ox, oy, oz)) {
                     ++nvalid;
                     if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {
-                        ++ncrop;
+                        crop = true; ++ncrop;
                         mnx = fminf(mnx, ox); mny = fminf(mny, oy); mnz = fminf(mnz, oz);
                         mxx = fmaxf(mxx, ox); mxy = fmaxf(mxy, oy); mxz = fmaxf(mxz, oz);
-                        const int i = gr * W + gc, i0 = gr * W + c0;
-                        atomicAdd(&s.rowcnt[(i >> 10) != (i0 >> 10) ? 1 : 0][tr], 1);
                     }
+                }
+            }
+            const unsigned bc = __ballot_sync(0xffffffffu, crop);
+            const unsigned bi = __ballot_sync(0xffffffffu, inside);
+            const unsigned bv = __ballot_sync(0xffffffffu, inside && gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(oz));
+            if (lane == 0) {
+                s.imask[tr] = bi; s.vmask[tr] = bv;
+                if (bc) {
+                    const int i0 = gr * W + c0, left = 1024 - (i0 & 1023);               /* pixels of this row inside i0's block */
+                    const unsigned lo = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+                    int *vc = d.vcnt + (size_t)f * d.nblk + (i0 >> 10);
+                    if (bc & lo) atomicAdd(vc, __popc(bc & lo));
+                    if (bc & ~lo) atomicAdd(vc + 1, __popc(bc & ~lo));
                 }
             }
         }
         nvalid = __reduce_add_sync(0xffffffffu, nvalid); ncrop = __reduce_add_sync(0xffffffffu, ncrop);
-        if (__any_sync(0xffffffffu, ncrop != 0)) {
+        if (ncrop) {                                                       /* warp-uniform */
             const int a0 = __reduce_min_sync(0xffffffffu, sp_f2ord(mnx)), a1 = __reduce_min_sync(0xffffffffu, sp_f2ord(mny)), a2 = __reduce_min_sync(0xffffffffu, sp_f2ord(mnz));
             const int b0 = __reduce_max_sync(0xffffffffu, sp_f2ord(mxx)), b1 = __reduce_max_sync(0xffffffffu, sp_f2ord(mxy)), b2 = __reduce_max_sync(0xffffffffu, sp_f2ord(mxz));
-            if ((tid & 31) == 0 && ncrop) {
+            if (lane == 0) {
                 atomicAdd(&d.counts[f * SP_NCOUNT + 2], ncrop);
                 int *mm = d.mm + f * 8;
                 atomicMin(mm + 0, a0); atomicMin(mm + 1, a1); atomicMin(mm + 2, a2);
                 atomicMax(mm + 3, b0); atomicMax(mm + 4, b1); atomicMax(mm + 5, b2);
             }
         }
-        if ((tid & 31) == 0 && nvalid) atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
-    }
-    __syncthreads();
-    if (tid < 2 * K1_TH) {
-        const int tr = tid & (K1_TH - 1), hi = tid >> 5, c = s.rowcnt[hi][tr];
-        if (c) atomicAdd(&d.vcnt[(size_t)f * d.nblk + (((r0 + tr) * W + c0) >> 10) + hi], c);
+        if (lane == 0 && nvalid) atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
     }
 
-    /* S1: depth-change flags on the lateral coordinate z (reference quirk), halo 4 */
-    for (int e = tid; e < K1_FH * K1_FW; e += K1_THREADS) {
-        const int rr = e / K1_FW, cc = e - rr * K1_FW;
-        const int se = (rr + 1) * K1_RW + cc + 1;
+    /* S1: depth-change flags on the lateral coordinate z (reference quirk), halo 4, as bit rows: one warp per flag row for
+     * columns 0..31 (the ballot is the row), then the eight tail columns of four rows per warp */
+    for (int fr = wid; fr < K1_FH; fr += 8) {
+        const int se = (fr + 1) * K1_RW + lane + 1;
         const float zc = s.sz[se];
         const bool z0 = k1_bad_pair(zc, s.sz[se + 1]) || k1_bad_pair(s.sz[se - 1], zc) ||
                         k1_bad_pair(zc, s.sz[se + K1_RW]) || k1_bad_pair(s.sz[se - K1_RW], zc);
-        s.zero[e] = z0 ? 1 : 0;
+        const unsigned b = __ballot_sync(0xffffffffu, z0);
+        if (lane == 0) s.zlo[fr] = b;
+    }
+    for (int q = wid; q < K1_FH / 4; q += 8) {
+        const int fr = q * 4 + (lane >> 3);
+        const int se = (fr + 1) * K1_RW + 32 + (lane & 7) + 1;
+        const float zc = s.sz[se];
+        const bool z0 = k1_bad_pair(zc, s.sz[se + 1]) || k1_bad_pair(s.sz[se - 1], zc) ||
+                        k1_bad_pair(zc, s.sz[se + K1_RW]) || k1_bad_pair(s.sz[se - K1_RW], zc);
+        const unsigned b = __ballot_sync(0xffffffffu, z0);
+        if ((lane & 7) == 0) s.zhi[fr] = (b >> (lane & 24)) & 255u;
     }
     /* S4 (independent of S1): gradient fields, halo 2 */
-    for (int e = tid; e < K1_GH * K1_GW; e += K1_THREADS) {
-        const int rr = e / K1_GW, cc = e - rr * K1_GW;
-        const int se = (rr + 3) * K1_RW + cc + 3, xe = (rr + 1) * K1_XW + cc + 1;
-        const float ax = s.sx[xe + 1] - s.sx[xe - 1], ay = s.sy[xe + 1] - s.sy[xe - 1], az = s.sz[se + 1] - s.sz[se - 1];
-        const float bx = s.sx[xe + K1_XW] - s.sx[xe - K1_XW], by = s.sy[xe + K1_XW] - s.sy[xe - K1_XW], bz = s.sz[se + K1_RW] - s.sz[se - K1_RW];
-        const bool fa = sp_finite(ax + (ay + az)), fb = sp_finite(bx + (by + bz));
-        s.gx[0][e] = fa ? ax : 0.0f; s.gx[1][e] = fa ? ay : 0.0f; s.gx[2][e] = fa ? az : 0.0f;
-        s.gy[0][e] = fb ? bx : 0.0f; s.gy[1][e] = fb ? by : 0.0f; s.gy[2][e] = fb ? bz : 0.0f;
-        s.fl[e] = (unsigned char)((fa ? 1 : 0) | (fb ? 2 : 0));
-    }
-    __syncthreads();
-    /* S2: horizontal distance to the nearest flagged pixel, capped at 5 */
-    for (int e = tid; e < K1_FH * K1_TW; e += K1_THREADS) {
-        const int rr = e / K1_TW, cc = e - rr * K1_TW;
-        const unsigned char *row = &s.zero[rr * K1_FW + cc + 4];
-        int h = 5;
-        if (row[0]) h = 0;
-        else if (row[-1] | row[1]) h = 1;
-        else if (row[-2] | row[2]) h = 2;
-        else if (row[-3] | row[3]) h = 3;
-        else if (row[-4] | row[4]) h = 4;
-        s.hd[e] = (unsigned char)h;
-    }
-    __syncthreads();
-
-    /* S3: smoothing size per owned pixel.  Pixels without a normal (invalid, border, next to a depth discontinuity: about a
-     * third of the tile) get their NaN here; the others are compacted into one list per window size, so that the box sums
-     * below run with full warps and fixed trip counts.  kcat[a][h]: rect size implied by a flagged pixel at row distance a,
-     * column distance h (chamfer 1.0/1.4: d = 1.4*min + (max-min); d<=2 -> 0 (NaN), (2,3) -> 2, [3,4) -> 3, [4,5) -> 4, >=5 -> 5) */
-    const unsigned kcat0 = 0x543000u, kcat1 = 0x543200u, kcat2 = 0x543220u, kcat3 = 0x554333u, kcat4 = 0x555444u;
-    const size_t tile_base = (size_t)f * N + (size_t)r0 * W + c0;
-    for (int e = tid; e < K1_TH * K1_TW; e += K1_THREADS) {
-        const int rr = e / K1_TW, cc = e - rr * K1_TW;
-        const int gr = r0 + rr, gc = c0 + cc;
-        const bool inside = gr < H && gc < W;
-        int k = 0;
-        if (inside && gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO])) {
-            const unsigned char *col = &s.hd[(rr + 4) * K1_TW + cc];
-            k = 5;
-            k = min(k, (int)((kcat0 >> (4 * col[0])) & 15u));
-            k = min(k, (int)((kcat1 >> (4 * min(col[-K1_TW], col[K1_TW]))) & 15u));
-            k = min(k, (int)((kcat2 >> (4 * min(col[-2 * K1_TW], col[2 * K1_TW]))) & 15u));
-            k = min(k, (int)((kcat3 >> (4 * min(col[-3 * K1_TW], col[3 * K1_TW]))) & 15u));
-            k = min(k, (int)((kcat4 >> (4 * min(col[-4 * K1_TW], col[4 * K1_TW]))) & 15u));
+    {
+        int rr = tid / K1_GW, cc = tid - rr * K1_GW;
+        for (int e = tid; e < K1_GH * K1_GW; e += K1_THREADS) {
+            const int se = (rr + 3) * K1_RW + cc + 3, xe = (rr + 1) * K1_XW + cc + 1;
+            const float ax = s.sx[xe + 1] - s.sx[xe - 1], ay = s.sy[xe + 1] - s.sy[xe - 1], az = s.sz[se + 1] - s.sz[se - 1];
+            const float bx = s.sx[xe + K1_XW] - s.sx[xe - K1_XW], by = s.sy[xe + K1_XW] - s.sy[xe - K1_XW], bz = s.sz[se + K1_RW] - s.sz[se - K1_RW];
+            const bool fa = sp_finite(ax + (ay + az)), fb = sp_finite(bx + (by + bz));
+            s.gx[0][e] = fa ? ax : 0.0f; s.gx[1][e] = fa ? ay : 0.0f; s.gx[2][e] = fa ? az : 0.0f;
+            s.gy[0][e] = fb ? bx : 0.0f; s.gy[1][e] = fb ? by : 0.0f; s.gy[2][e] = fb ? bz : 0.0f;
+            s.fl[e] = (unsigned char)((fa ? 1 : 0) | (fb ? 2 : 0));
+            cc += K1_THREADS % K1_GW; rr += K1_THREADS / K1_GW;
+            if (cc >= K1_GW) { cc -= K1_GW; ++rr; }
         }
-        if (inside && k < 2) { const size_t gi = tile_base + (size_t)rr * W + cc; d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan; }
-        /* warp-aggregated appends: one shared atomic per warp and list */
-        const unsigned lanebit = 1u << (tid & 31), lt = lanebit - 1u;
+    }
+    __syncthreads();
+    /* S2: a flagged pixel within h columns, h = 0..4, for every flag row (PCL's distance map along the row, capped at 5) */
+    if (tid < K1_FH) {
+        unsigned long long m = (unsigned long long)s.zlo[tid] | ((unsigned long long)s.zhi[tid] << 32);
+        s.dil[0][tid] = m;
 #pragma unroll
-        for (int kk = 5; kk >= 3; --kk) {                                  /* kk == 3 stands for the windows of 3 and 2 */
-            const bool mine = kk == 3 ? (k == 3 || k == 2) : k == kk;
-            const unsigned bm = __ballot_sync(0xffffffffu, mine);
-            if (bm) {
-                int *ctr = kk == 5 ? &s.n5 : (kk == 4 ? &s.n4 : &s.n32);
-                int base = 0;
-                if ((bm & lt) == 0 && (bm & lanebit)) base = atomicAdd(ctr, __popc(bm));
-                base = __shfl_sync(0xffffffffu, base, __ffs(bm) - 1);
-                if (mine) {
-                    const int pos = base + __popc(bm & lt);
-                    if (kk == 5) s.list[pos] = (unsigned short)e;
-                    else if (kk == 4) s.list[K1_TH * K1_TW - 1 - pos] = (unsigned short)e;
-                    else if (pos < K1_TH * K1_TW / 2) s.list2[pos] = (unsigned short)(e | (k << 12));
-                    else if (k == 3) k1_normal<3>(s, d, e, tile_base, W);      /* list full (pathological tile): in place */
-                    else k1_normal<2>(s, d, e, tile_base, W);
-                }
-            }
+        for (int h = 1; h < 5; ++h) { m |= (m << 1) | (m >> 1); s.dil[h][tid] = m; }
+    }
+    __syncthreads();
+    /* S3: smoothing size per owned pixel, one thread per tile row.  A flagged pixel at row distance a and column distance h
+     * allows a window of kcat[a][h] (chamfer 1.0/1.4: d = 1.4*min + (max-min); d<=2 -> 0 (NaN), (2,3) -> 2, [3,4) -> 3, [4,5) -> 4,
+     * >=5 -> 5):  a=0: 0 0 0 3 4 5 | a=1: 0 0 2 3 4 5 | a=2: 0 2 2 3 4 5 | a=3: 3 3 3 4 5 5 | a=4: 4 4 4 5 5 5  (h = 0..5).
+     * "window <= k" is therefore an OR of dilated rows; the list offsets of each row come from a warp scan of the counts. */
+    if (tid < K1_TH) {
+        const int r = tid + 4;
+        const unsigned long long (*D)[K1_FH] = s.dil;
+        const unsigned long long z0 = D[2][r] | D[1][r - 1] | D[1][r + 1] | D[0][r - 2] | D[0][r + 2];
+        const unsigned long long z2 = D[2][r] | D[2][r - 1] | D[2][r + 1] | D[2][r - 2] | D[2][r + 2];
+        const unsigned long long z3 = D[3][r] | D[3][r - 1] | D[3][r + 1] | D[3][r - 2] | D[3][r + 2] | D[2][r - 3] | D[2][r + 3];
+        const unsigned long long z4 = D[4][r] | D[4][r - 1] | D[4][r + 1] | D[4][r - 2] | D[4][r + 2] | D[3][r - 3] | D[3][r + 3] | D[2][r - 4] | D[2][r + 4];
+        const unsigned v = s.vmask[tid];
+        const unsigned k5 = v & ~(unsigned)(z4 >> 4), k4 = v & (unsigned)((z4 & ~z3) >> 4), k3 = v & (unsigned)((z3 & ~z2) >> 4), k2 = v & (unsigned)((z2 & ~z0) >> 4);
+        s.kmask[0][tid] = k5; s.kmask[1][tid] = k4; s.kmask[2][tid] = k3; s.kmask[3][tid] = k2;
+        int c5 = __popc(k5), c4 = __popc(k4), c32 = __popc(k3 | k2);
+        int i5 = c5, i4 = c4, i32 = c32;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t5 = __shfl_up_sync(0xffffffffu, i5, o), t4 = __shfl_up_sync(0xffffffffu, i4, o), t32 = __shfl_up_sync(0xffffffffu, i32, o);
+            if (lane >= o) { i5 += t5; i4 += t4; i32 += t32; }
+        }
+        s.base[0][tid] = (unsigned short)(i5 - c5); s.base[1][tid] = (unsigned short)(i4 - c4); s.base[2][tid] = (unsigned short)(i32 - c32);
+        if (tid == K1_TH - 1) { s.n5 = i5; s.n4 = i4; s.n32 = i32; }
+    }
+    __syncthreads();
+    /* Pixels without a normal (invalid, border, next to a depth discontinuity: about a third of the tile) get their NaN here;
+     * the others go into one list per window size, so that the box sums below run with full warps and fixed trip counts. */
+#pragma unroll
+    for (int it = 0; it < K1_TH / 8; ++it) {
+        const int tr = it * 8 + wid, e = tr * K1_TW + lane;
+        const unsigned k5 = s.kmask[0][tr], k4 = s.kmask[1][tr], k3 = s.kmask[2][tr], k2 = s.kmask[3][tr], bit = 1u << lane;
+        if (s.imask[tr] & ~(k5 | k4 | k3 | k2) & bit) { const size_t gi = tile_base + (size_t)tr * W + lane; d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan; }
+        if (k5 & bit) s.list[s.base[0][tr] + __popc(k5 & lt)] = (unsigned short)e;
+        else if (k4 & bit) s.list[K1_TH * K1_TW - 1 - (s.base[1][tr] + __popc(k4 & lt))] = (unsigned short)e;
+        else if ((k3 | k2) & bit) {
+            const int pos = s.base[2][tr] + __popc((k3 | k2) & lt);
+            if (pos < K1_TH * K1_TW / 2) s.list2[pos] = (unsigned short)(e | ((k3 & bit) ? (3 << 12) : (2 << 12)));
+            else if (k3 & bit) k1_normal<3>(s, d, e, tile_base, W);          /* list full (pathological tile): in place */
+            else k1_normal<2>(s, d, e, tile_base, W);
         }
     }
     __syncthreads();

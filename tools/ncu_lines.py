@@ -18,15 +18,19 @@ def main():
             hdr = r
         elif hdr and len(r) == len(hdr) and r[2] == "-":          # a source line row (its SASS rows carry an address)
             ci, ct, cn = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
+            cw, cx = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Excessive")
             try:
-                out.append((int(r[ci]), int(r[ct]), int(r[cn]), "%s:%s" % (fname, r[0]), r[1].strip()[:100]))
+                out.append((int(r[ci]), int(r[ct]), int(r[cn]), "%s:%s" % (fname, r[0]), r[1].strip()[:90], int(r[cw] or 0), int(r[cx] or 0)))
             except ValueError:
                 pass
     tot = sum(o[0] for o in out)
     samp = sum(o[2] for o in out)
-    print("warp instructions %d, samples %d" % (tot, samp))
+    wav = sum(o[5] for o in out)
+    print("warp instructions %d, samples %d, shared-memory wavefronts %d (excessive %d)" % (tot, samp, wav, sum(o[6] for o in out)))
     for o in sorted(out, reverse=True)[:top]:
-        print("%5.1f%% inst  %5.1f%% samp  thr/inst %4.1f  %-18s %s" % (100.0 * o[0] / max(tot, 1), 100.0 * o[2] / max(samp, 1), o[1] / max(o[0], 1), o[3], o[4]))
+        print("%5.1f%% inst  %5.1f%% samp  thr/inst %4.1f  smem wav %5.1f%% (x%.2f)  %-18s %s" % (
+            100.0 * o[0] / max(tot, 1), 100.0 * o[2] / max(samp, 1), o[1] / max(o[0], 1), 100.0 * o[5] / max(wav, 1),
+            o[5] / max(o[5] - o[6], 1), o[3], o[4]))
 
 
 if __name__ == "__main__":
