@@ -31,21 +31,24 @@
 #define K1_GH (K1_TH + 4)
 #define K1_THREADS 256
 
-struct K1Smem {                           /* 55.6 KB: four CTAs per SM */
-    float sz[K1_RH * K1_RW];
+#define K1_BAND 8                         /* tile rows per column-sum band of the exact path */
+struct K1Smem {                           /* 54.9 KB: four CTAs per SM */
+    float sz[K1_RH * K1_RW];              /* sz, sx, sy are contiguous: the exact path re-uses them as its column-sum band */
     float sx[K1_XH * K1_XW], sy[K1_XH * K1_XW];
     float gx[3][K1_GH * K1_GW], gy[3][K1_GH * K1_GW];
     unsigned long long dil[5][K1_FH];     /* bit rows of the flag region (bit c = column c): depth-change pixels dilated by 0..4 columns */
     unsigned zlo[K1_FH], zhi[K1_FH];      /* the undilated rows as the ballots deliver them: columns 0..31 and 32..39 */
+    unsigned falo[K1_GH], fahi[K1_GH], fblo[K1_GH], fbhi[K1_GH];   /* finite dx / dy gradient elements per gradient row, same split */
     unsigned kmask[4][K1_TH];             /* per tile row: pixels whose smoothing window is 5, 4, 3, 2 */
     unsigned vmask[K1_TH], imask[K1_TH];  /* pixels that may get a normal (image border, finite z); pixels inside the image */
     unsigned short base[3][K1_TH];        /* where a row's window-5 / window-4 / window-3-and-2 pixels start in their list */
-    unsigned char fl[K1_GH * K1_GW];      /* finite flags of the gradient elements: bit 0 = dx, bit 1 = dy */
     unsigned short list[K1_TH * K1_TW];   /* pixels that get a normal, by window size: 5 from the front, 4 from the back */
     unsigned short list2[K1_TH * K1_TW / 2];   /* windows of 3 and 2, tagged (pixel | k << 12); a tile with more takes them in place */
     int n5, n4, n32, pad;
 };
 static_assert(K1_FW <= 64 && K1_TW == 32, "bit rows: one 64-bit word per flag row, one warp lane per tile column");
+static_assert(6 * K1_BAND * K1_GW * sizeof(double) <= (K1_RH * K1_RW + 2 * K1_XH * K1_XW) * sizeof(float), "column-sum band must fit in sz + sx + sy");
+static_assert(K1_TH % K1_BAND == 0 && 6 * K1_GW <= K1_THREADS, "one thread per (channel, gradient column)");
 
 __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
 {
@@ -54,8 +57,29 @@ __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
     return (fabsf(za - zb) > thr) || !sp_finite(za) || !sp_finite(zb);
 }
 
+/* cross product of the two summed gradients, normalisation, flip towards the origin (PCL's view point), store */
+__device__ __forceinline__ void k1_finish(const SpDev &d, size_t gi, float px, float py, float pz,
+                                          double sgx0, double sgx1, double sgx2, double sgy0, double sgy1, double sgy2)
+{
+    float onx = __int_as_float(0x7fc00000), ony = onx, onz = onx;
+    const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
+    const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
+    const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
+    const double L = n0 * n0 + (n1 * n1 + n2 * n2);
+    if (L != 0.0) {
+        const double sq = sqrt(L);
+        float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
+        const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
+        const float cs = (vx * fx + vy * fy + vz * fz);
+        if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
+        onx = fx; ony = fy; onz = fz;
+    }
+    d.nx[gi] = onx; d.ny[gi] = ony; d.nz[gi] = onz;
+}
+
 /* k x k box sums of the two gradient fields around tile pixel e, in the oracle's order (rows top to bottom of row sums
- * left to right, double), then cross product, normalisation and flip; stores the normal straight to global memory */
+ * left to right, double), then k1_finish.  Only pixels whose two windows hold at least one finite gradient element each get
+ * here (the window masks of S3 take care of that). */
 template <int K>
 __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e, size_t tile_base, int W)
 {
@@ -63,7 +87,6 @@ __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e
     const int half = K >> 1;
     const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
     double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
-    unsigned orf = 0;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
         double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
@@ -73,29 +96,20 @@ __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e
             const int ge = gb + b;
             rx0 += (double)s.gx[0][ge]; rx1 += (double)s.gx[1][ge]; rx2 += (double)s.gx[2][ge];
             ry0 += (double)s.gy[0][ge]; ry1 += (double)s.gy[1][ge]; ry2 += (double)s.gy[2][ge];
-            orf |= s.fl[ge];
         }
         sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
     }
-    float onx = __int_as_float(0x7fc00000), ony = onx, onz = onx;
-    if (orf == 3u) {                                   /* both windows hold at least one finite element */
-        const double n0 = sgy1 * sgx2 - sgy2 * sgx1;
-        const double n1 = sgy2 * sgx0 - sgy0 * sgx2;
-        const double n2 = sgy0 * sgx1 - sgy1 * sgx0;
-        const double L = n0 * n0 + (n1 * n1 + n2 * n2);
-        if (L != 0.0) {
-            const int sxe = (rr + 3) * K1_XW + cc + 3;
-            const float px = s.sx[sxe], py = s.sy[sxe], pz = s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO];
-            const double sq = sqrt(L);
-            float fx = (float)(n0 / sq), fy = (float)(n1 / sq), fz = (float)(n2 / sq);
-            const float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
-            const float cs = (vx * fx + vy * fy + vz * fz);
-            if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
-            onx = fx; ony = fy; onz = fz;
-        }
-    }
-    const size_t gi = tile_base + (size_t)rr * W + cc;
-    d.nx[gi] = onx; d.ny[gi] = ony; d.nz[gi] = onz;
+    const int sxe = (rr + 3) * K1_XW + cc + 3;
+    k1_finish(d, tile_base + (size_t)rr * W + cc, s.sx[sxe], s.sy[sxe], s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO], sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
+}
+
+/* A coordinate that is NaN, zero, or 2^-21 <= |c| < 8 is a multiple of 2^-44 below 8.  If every coordinate of the tile is like
+ * that, every gradient element (a float difference of two of them) is a multiple of 2^-44 of magnitude <= 16, and any sum of up to
+ * 30 of them is a multiple of 2^-44 below 2^9: 53 bits, exact in double whatever the order of the additions. */
+__device__ __forceinline__ bool k1_inexact_risk(float c)
+{
+    const unsigned u = __float_as_uint(c) & 0x7fffffffu;
+    return !(u - 0x35000000u < 0x41000000u - 0x35000000u || u == 0u || u > 0x7f800000u);
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
@@ -111,6 +125,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
     const size_t tile_base = (size_t)f * N + (size_t)r0 * W + c0;
 
     /* S0: load tile + halo, level, mask -> shared memory (flat index, row / column kept incrementally: 256 = 6 * 42 + 4) */
+    bool risk = false;
     {
         float R[9];
         const bool rot = d.R != nullptr;
@@ -136,13 +151,14 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
                 if (__vcmpeq4(__float_as_uint(p.w) | 0xff000000u, 0u)) { ox = oy = oz = qnan; }
             }
             s.sz[e] = oz;
+            risk |= k1_inexact_risk(ox) | k1_inexact_risk(oy) | k1_inexact_risk(oz);
             const unsigned xr = (unsigned)(rr - 2), xc = (unsigned)(cc - 2);       /* x, y keep a halo of 3 */
             if (xr < (unsigned)K1_XH && xc < (unsigned)K1_XW) { s.sx[xr * K1_XW + xc] = ox; s.sy[xr * K1_XW + xc] = oy; }
             cc += K1_THREADS % K1_RW; rr += K1_THREADS / K1_RW;
             if (cc >= K1_RW) { cc -= K1_RW; ++rr; }
         }
     }
-    __syncthreads();
+    const bool exact = __syncthreads_or(risk) == 0;      /* box sums of this tile are exact in double in any order */
 
     /* S0b: the owned pixels, one warp per tile row (lane = column): levelled xyz out, crop statistics of
      * passThroughCloudANDNormal / getMinMax3D, cropped pixels per 1024-pixel block for the voxel stage, row masks */
@@ -216,20 +232,24 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         const unsigned b = __ballot_sync(0xffffffffu, z0);
         if ((lane & 7) == 0) s.zhi[fr] = (b >> (lane & 24)) & 255u;
     }
-    /* S4 (independent of S1): gradient fields, halo 2 */
-    {
-        int rr = tid / K1_GW, cc = tid - rr * K1_GW;
-        for (int e = tid; e < K1_GH * K1_GW; e += K1_THREADS) {
+    /* S4 (independent of S1): gradient fields, halo 2, same row-aligned passes: columns 0..31 of a gradient row per warp, then
+     * the four tail columns of eight rows per warp; the ballots are the rows of finite elements */
+    for (int q = wid; q < K1_GH + (K1_GH + 7) / 8; q += 8) {
+        const bool tail = q >= K1_GH;
+        const int rr = tail ? (q - K1_GH) * 8 + (lane >> 2) : q, cc = tail ? 32 + (lane & 3) : lane;
+        bool fa = false, fb = false;
+        if (rr < K1_GH) {
+            const int e = rr * K1_GW + cc;
             const int se = (rr + 3) * K1_RW + cc + 3, xe = (rr + 1) * K1_XW + cc + 1;
             const float ax = s.sx[xe + 1] - s.sx[xe - 1], ay = s.sy[xe + 1] - s.sy[xe - 1], az = s.sz[se + 1] - s.sz[se - 1];
             const float bx = s.sx[xe + K1_XW] - s.sx[xe - K1_XW], by = s.sy[xe + K1_XW] - s.sy[xe - K1_XW], bz = s.sz[se + K1_RW] - s.sz[se - K1_RW];
-            const bool fa = sp_finite(ax + (ay + az)), fb = sp_finite(bx + (by + bz));
+            fa = sp_finite(ax + (ay + az)); fb = sp_finite(bx + (by + bz));
             s.gx[0][e] = fa ? ax : 0.0f; s.gx[1][e] = fa ? ay : 0.0f; s.gx[2][e] = fa ? az : 0.0f;
             s.gy[0][e] = fb ? bx : 0.0f; s.gy[1][e] = fb ? by : 0.0f; s.gy[2][e] = fb ? bz : 0.0f;
-            s.fl[e] = (unsigned char)((fa ? 1 : 0) | (fb ? 2 : 0));
-            cc += K1_THREADS % K1_GW; rr += K1_THREADS / K1_GW;
-            if (cc >= K1_GW) { cc -= K1_GW; ++rr; }
         }
+        const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
+        if (!tail) { if (lane == 0) { s.falo[rr] = ba; s.fblo[rr] = bb; } }
+        else if ((lane & 3) == 0 && rr < K1_GH) { s.fahi[rr] = (ba >> (lane & 28)) & 15u; s.fbhi[rr] = (bb >> (lane & 28)) & 15u; }
     }
     __syncthreads();
     /* S2: a flagged pixel within h columns, h = 0..4, for every flag row (PCL's distance map along the row, capped at 5) */
@@ -251,8 +271,23 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         const unsigned long long z2 = D[2][r] | D[2][r - 1] | D[2][r + 1] | D[2][r - 2] | D[2][r + 2];
         const unsigned long long z3 = D[3][r] | D[3][r - 1] | D[3][r + 1] | D[3][r - 2] | D[3][r + 2] | D[2][r - 3] | D[2][r + 3];
         const unsigned long long z4 = D[4][r] | D[4][r - 1] | D[4][r + 1] | D[4][r - 2] | D[4][r + 2] | D[3][r - 3] | D[3][r + 3] | D[2][r - 4] | D[2][r + 4];
+        /* a normal needs one finite element in each gradient window (PCL's finite-element counts): rows tid + a of the gradient
+         * region, columns cc + b; windows of 5: a, b = 0..4; 4: 0..3; 3: 1..3; 2: 1..2 */
+        unsigned long long fa[5], fb[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            fa[a] = (unsigned long long)s.falo[tid + a] | ((unsigned long long)s.fahi[tid + a] << 32);
+            fb[a] = (unsigned long long)s.fblo[tid + a] | ((unsigned long long)s.fbhi[tid + a] << 32);
+        }
+        const unsigned long long a2 = fa[1] | fa[2], a3 = a2 | fa[3], a4 = a3 | fa[0], a5 = a4 | fa[4];
+        const unsigned long long b2 = fb[1] | fb[2], b3 = b2 | fb[3], b4 = b3 | fb[0], b5 = b4 | fb[4];
+        const unsigned w2 = (unsigned)((a2 >> 1) | (a2 >> 2)) & (unsigned)((b2 >> 1) | (b2 >> 2));
+        const unsigned w3 = (unsigned)((a3 >> 1) | (a3 >> 2) | (a3 >> 3)) & (unsigned)((b3 >> 1) | (b3 >> 2) | (b3 >> 3));
+        const unsigned w4 = (unsigned)(a4 | (a4 >> 1) | (a4 >> 2) | (a4 >> 3)) & (unsigned)(b4 | (b4 >> 1) | (b4 >> 2) | (b4 >> 3));
+        const unsigned w5 = (unsigned)(a5 | (a5 >> 1) | (a5 >> 2) | (a5 >> 3) | (a5 >> 4)) & (unsigned)(b5 | (b5 >> 1) | (b5 >> 2) | (b5 >> 3) | (b5 >> 4));
         const unsigned v = s.vmask[tid];
-        const unsigned k5 = v & ~(unsigned)(z4 >> 4), k4 = v & (unsigned)((z4 & ~z3) >> 4), k3 = v & (unsigned)((z3 & ~z2) >> 4), k2 = v & (unsigned)((z2 & ~z0) >> 4);
+        const unsigned k5 = v & w5 & ~(unsigned)(z4 >> 4), k4 = v & w4 & (unsigned)((z4 & ~z3) >> 4), k3 = v & w3 & (unsigned)((z3 & ~z2) >> 4),
+                       k2 = v & w2 & (unsigned)((z2 & ~z0) >> 4);
         s.kmask[0][tid] = k5; s.kmask[1][tid] = k4; s.kmask[2][tid] = k3; s.kmask[3][tid] = k2;
         int c5 = __popc(k5), c4 = __popc(k4), c32 = __popc(k3 | k2);
         int i5 = c5, i4 = c4, i32 = c32;
@@ -282,14 +317,52 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         }
     }
     __syncthreads();
-    /* S5: box sums + normal, one pass per window size */
+    /* S5: box sums + normal, one pass per window size.  Windows of 4, 3, 2 (and of 5 in a tile without the exactness
+     * guarantee) take the direct sums ... */
     const int n5 = s.n5, n4 = s.n4, n32 = min(s.n32, K1_TH * K1_TW / 2);
-    for (int i = tid; i < n5; i += K1_THREADS) k1_normal<5>(s, d, s.list[i], tile_base, W);
+    if (!exact) { for (int i = tid; i < n5; i += K1_THREADS) k1_normal<5>(s, d, s.list[i], tile_base, W); }
     for (int i = tid; i < n4; i += K1_THREADS) k1_normal<4>(s, d, s.list[K1_TH * K1_TW - 1 - i], tile_base, W);
     for (int i = tid; i < n32; i += K1_THREADS) {
         const int code = s.list2[i];
         if ((code >> 12) == 3) k1_normal<3>(s, d, code & 0xfff, tile_base, W);
         else k1_normal<2>(s, d, code & 0xfff, tile_base, W);
+    }
+    if (!exact || n5 == 0) return;                                          /* CTA-uniform */
+    /* ... the windows of 5 of an exact tile take separable sums, K1_BAND tile rows at a time: a thread per (channel, gradient
+     * column) slides a 5-row column sum down the band (shared memory: the band re-uses sz / sx / sy, whose last readers were
+     * the direct sums above), then a thread per pixel adds five neighbouring column sums per channel.  Exact sums: same bits
+     * as the ordered sums of k1_normal<5>.  The point itself (for the flip) comes back from global memory. */
+    double *csum = reinterpret_cast<double *>(k1_raw);                      /* [6][K1_BAND][K1_GW] */
+    const int ch = tid / K1_GW, col = tid - ch * K1_GW;
+    const float *g = ch < 3 ? s.gx[ch] : s.gy[ch < 6 ? ch - 3 : 0];
+    for (int b0 = 0; b0 < K1_TH; b0 += K1_BAND) {
+        const int p0 = s.base[0][b0], p1 = b0 + K1_BAND < K1_TH ? s.base[0][b0 + K1_BAND] : n5;
+        __syncthreads();                                                    /* previous band read / direct sums done with sz, sx, sy */
+        if (p1 > p0 && ch < 6) {
+            float v[K1_BAND + 4];
+#pragma unroll
+            for (int a = 0; a < K1_BAND + 4; ++a) v[a] = g[(b0 + a) * K1_GW + col];
+            double w = (double)v[0] + (double)v[1] + (double)v[2] + (double)v[3];
+#pragma unroll
+            for (int i = 0; i < K1_BAND; ++i) {
+                w += (double)v[i + 4];
+                csum[(ch * K1_BAND + i) * K1_GW + col] = w;
+                w -= (double)v[i];
+            }
+        }
+        __syncthreads();
+        for (int i = p0 + tid; i < p1; i += K1_THREADS) {
+            const int e = s.list[i], rr = e / K1_TW, cc = e - rr * K1_TW;
+            const double *c = csum + (rr - b0) * K1_GW + cc;
+            double sg[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double *q = c + k * K1_BAND * K1_GW;
+                sg[k] = q[0] + q[1] + q[2] + q[3] + q[4];
+            }
+            const size_t gi = tile_base + (size_t)rr * W + cc;
+            k1_finish(d, gi, d.x[gi], d.y[gi], d.z[gi], sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
+        }
     }
 }
 

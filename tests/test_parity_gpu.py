@@ -363,3 +363,28 @@ def test_voxel_sort_64bit_key_path(sp, orc, synth, monkeypatch):
         bad = compare_frame(ctx, i, res[i], o)
         assert not bad, "frame %d\n" % i + "\n".join(bad[:20])
     ctx.close()
+
+
+def test_normals_without_the_exactness_guarantee(sp, orc, synth):
+    """k_ingest_normals takes separable box sums only in tiles whose coordinates make every double sum exact (NaN, zero, or
+    2^-21 <= |c| < 8); other tiles take the ordered sums.  A scene scaled by four (coordinates up to 18 m) and one sprinkled with
+    tiny coordinates must still match the oracle bit for bit."""
+    rec, R = synth.make_frame(12)
+    big = rec.copy()
+    for k in ("x", "y", "z"):
+        big[k] = big[k] * np.float32(4.0)
+    tiny = rec.copy()
+    rng = np.random.default_rng(5)
+    idx = rng.choice(tiny.shape[0], 4000, replace=False)
+    tiny["x"][idx[:2000]] = np.float32(3e-9)
+    tiny["z"][idx[2000:]] = np.float32(-7e-8)
+    p = dict(sp.DEFAULT_PARAMS)
+    p.update(x_min=-20.0, x_max=20.0, y_min=-20.0, y_max=20.0, z_min=-20.0, z_max=20.0)
+    ctx = sp.Context(p, device=0, width=512, height=424, max_batch=2)
+    res = ctx.process_frames(np.stack([big, tiny]), np.stack([R, R]))
+    for i, r in enumerate((big, tiny)):
+        o = orc.Oracle(p)
+        o.process(r, 512, 424, R)
+        bad = compare_frame(ctx, i, res[i], o)
+        assert not bad, "frame %d\n" % i + "\n".join(bad[:20])
+    ctx.close()
