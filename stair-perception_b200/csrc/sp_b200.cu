@@ -369,7 +369,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     d.nblk = (int)((N + 1023) / 1024);
 #define DA(ptr, n) if ((e = dalloc(ctx, &(ptr), (n))) != cudaSuccess) return fail("cudaMalloc " #ptr, e)
     DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
-    DA(d.x, BN); DA(d.y, BN); DA(d.z, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
+    DA(d.x, BN); DA(d.y, BN); DA(d.z, BN); DA(d.xyzw, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
     DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 2);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);

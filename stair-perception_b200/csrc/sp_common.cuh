@@ -76,6 +76,7 @@ struct SpDev {
     const float *R;            /* [B][9] or NULL */
     /* stage 1 */
     float *x, *y, *z, *nx, *ny, *nz;
+    float4 *xyzw;              /* [B][N] the same levelled points packed {x, y, z, 0}: one 32-byte sector per gathered point in the voxel stage */
     int *mm;                   /* [B][8] ordered-int min xyz, max xyz, + 2 pad */
     int *counts;               /* [B][SP_NCOUNT] */
     SpFrameGrid *grid;

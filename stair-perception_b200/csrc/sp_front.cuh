@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
             bool crop = false;
             if (inside) {
                 const size_t gi = tile_base + (size_t)tr * W + lane;
-                d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz;
+                d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz; d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
                 if (sp_finite3(ox, oy, oz)) {
                     ++nvalid;
                     if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {
@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
                 sg[k] = q[0] + q[1] + q[2] + q[3] + q[4];
             }
             const size_t gi = tile_base + (size_t)rr * W + cc;
-            k1_finish(d, gi, d.x[gi], d.y[gi], d.z[gi], sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
+            const float4 pw = d.xyzw[gi];
+            k1_finish(d, gi, pw.x, pw.y, pw.z, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
         }
     }
 }
@@ -480,7 +481,8 @@ __global__ void __launch_bounds__(256) k_voxel_key(SpDev d)
         bool ok = false; unsigned key = 0;
         if (i < N) {
             const size_t gi = (size_t)f * N + i;
-            const float px = d.x[gi], py = d.y[gi], pz = d.z[gi];
+            const float4 pw = d.xyzw[gi];
+            const float px = pw.x, py = pw.y, pz = pw.z;
             if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
                 const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
                 const int b = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
     const unsigned *keys32 = reinterpret_cast<const unsigned *>(d.key_b) + d.foff[f];
     auto key_at = [&](int t) -> unsigned long long { return k32 ? (unsigned long long)keys32[t] : keys64[t]; };
     const unsigned *vals = d.val_b + d.foff[f];
-    const float *X = d.x + base, *Y = d.y + base, *Z = d.z + base;
+    const float4 *P = d.xyzw + base;
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     for (int q = 0; q < 4; ++q) {
         const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
@@ -526,13 +528,14 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
         const unsigned long long key = j < M ? key_at(j) : 0ull;
         if (j < M && (j == 0 || key_at(j - 1) != key)) {
             float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-            for (int t = j; t < M && key_at(t) == key; ++t) { const unsigned p = vals[t]; sx += X[p]; sy += Y[p]; sz += Z[p]; ++n; }
+            for (int t = j; t < M && key_at(t) == key; ++t) { const float4 pw = P[vals[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
             const float fn = (float)n;
             const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
             float best = FLT_MAX;
             for (int t = j; t < j + n; ++t) {
                 const unsigned p = vals[t];
-                const float dx = cx - X[p], dy = cy - Y[p], dz = cz - Z[p];
+                const float4 pw = P[p];
+                const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
                 const float dis = dx * dx + dy * dy + dz * dz;
                 if (best > dis) { best = dis; rep = (int)p; }
             }
@@ -540,7 +543,8 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
             const float nx = d.nx[base + rep], ny = d.ny[base + rep], nz = d.nz[base + rep];
             if (sp_finite3(nx, ny, nz)) {
                 code |= SPC_NONAN; ++c1;
-                const float px = X[rep], py = Y[rep], pz = Z[rep];
+                const float4 pw = P[rep];
+                const float px = pw.x, py = pw.y, pz = pw.z;
                 if (px * px + py * py + pz * pz > d.c.noleg_th2) {
                     code |= SPC_NOLEG; ++c2;
                     if (nx >= d.c.h_ge || nx <= d.c.h_le) { code |= SPC_H; ++c3; }
@@ -609,10 +613,10 @@ __global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
         if (code & SPC_HEAD) { d.voxel_idx[base + b_head + ph] = rep; d.voxel_code[base + b_head + ph] = code; }
         b_head += tot;
         const int pH = sp_block_scan_flag((code & SPC_H) != 0, wsum, &tot);
-        if (code & SPC_H) d.pts[(size_t)(2 * f) * N + b_h + pH] = make_float4(d.x[base + rep], d.y[base + rep], d.z[base + rep], __int_as_float(rep));
+        if (code & SPC_H) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f) * N + b_h + pH] = pw; }
         b_h += tot;
         const int pV = sp_block_scan_flag((code & SPC_V) != 0, wsum, &tot);
-        if (code & SPC_V) d.pts[(size_t)(2 * f + 1) * N + b_v + pV] = make_float4(d.x[base + rep], d.y[base + rep], d.z[base + rep], __int_as_float(rep));
+        if (code & SPC_V) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f + 1) * N + b_v + pV] = pw; }
         b_v += tot;
     }
 }

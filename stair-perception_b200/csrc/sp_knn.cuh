@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_ingest_plain(SpDev d, int *knn_mm)
         const unsigned rgba = __float_as_uint(p.w);
         if ((rgba & 255u) == 0u || ((rgba >> 8) & 255u) == 0u || ((rgba >> 16) & 255u) == 0u) { ox = oy = oz = qnan; }
         const size_t gi = (size_t)f * N + i;
-        d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz;
+        d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz; d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
         d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan;
         bool crop = false;
         if (sp_finite3(ox, oy, oz)) {

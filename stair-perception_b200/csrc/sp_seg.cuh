@@ -43,39 +43,43 @@ __global__ void __launch_bounds__(256) k_cl_count(SpDev d)
     }
 }
 
-/* exclusive scan of one segment's bucket counts: one CTA of 1024 threads, 64 buckets per thread */
+/* exclusive scan of one segment's bucket counts: one CTA of 1024 threads, a warp per 2048 consecutive buckets, read and
+ * written as coalesced int4 rows of 128 buckets (pass 1: warp totals; pass 2, from L2: running scan row by row) */
 __global__ void __launch_bounds__(1024) k_cl_scan(SpDev d)
 {
     __shared__ int wsum[32];
     const int s = blockIdx.x;
     if (d.seg_n[s] == 0) return;
-    const int4 *cnt = reinterpret_cast<const int4 *>(d.ccnt + ((size_t)s << SP_HASH_BITS)) + threadIdx.x * 16;
-    int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
-    int4 v[16];
-    int tot = 0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { v[q] = cnt[q]; tot += v[q].x + v[q].y + v[q].z + v[q].w; }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[wid] = inc;
+    const int per_warp = (1 << SP_HASH_BITS) / 32, rows = per_warp / 128;
+    const int4 *cnt = reinterpret_cast<const int4 *>(d.ccnt + ((size_t)s << SP_HASH_BITS) + (size_t)wid * per_warp) + lane;
+    int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1) + (size_t)wid * per_warp;
+    int tot = 0;
+#pragma unroll 4
+    for (int q = 0; q < rows; ++q) { const int4 v = cnt[q * 32]; tot += (v.x + v.y) + (v.z + v.w); }
+    tot = __reduce_add_sync(0xffffffffu, tot);
+    if (lane == 0) wsum[wid] = tot;
     __syncthreads();
     if (wid == 0) {
         int w = wsum[lane], wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
         wsum[lane] = wi - w;
+        if (lane == 31) d.cstart[(size_t)s * ((1 << SP_HASH_BITS) + 1) + (1 << SP_HASH_BITS)] = wi;
     }
     __syncthreads();
-    int run = wsum[wid] + inc - tot;
-    int *o = start + threadIdx.x * 64;
+    int run = wsum[wid];                                                  /* buckets before this row */
+    for (int q = 0; q < rows; ++q) {
+        const int4 v = cnt[q * 32];
+        const int mine = (v.x + v.y) + (v.z + v.w);
+        int inc = mine;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        o[4 * q] = run; run += v[q].x; o[4 * q + 1] = run; run += v[q].y;
-        o[4 * q + 2] = run; run += v[q].z; o[4 * q + 3] = run; run += v[q].w;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        int r = run + inc - mine;
+        int *o = start + q * 128 + lane * 4;                             /* cstart rows start at an odd multiple of 4 bytes: scalar stores */
+        o[0] = r; r += v.x; o[1] = r; r += v.y; o[2] = r; r += v.z; o[3] = r;
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (threadIdx.x == 1023) start[1 << SP_HASH_BITS] = run;
 }
 
 __global__ void __launch_bounds__(256) k_cl_scatter(SpDev d)
