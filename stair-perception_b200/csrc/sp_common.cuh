@@ -160,3 +160,25 @@ __device__ __forceinline__ int sp_block_scan_flag(bool flag, int *warp_sums, int
     *total = warp_sums[32];
     return warp_sums[wid] + within;
 }
+
+/* the same for three flags at once, packed in 10-bit fields (a | b << 10 | c << 20): blockDim.x <= 1023 keeps every count in its field */
+__device__ __forceinline__ int sp_block_scan_flags3(bool fa, bool fb, bool fc, int *warp_sums, int *total)
+{
+    const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb), bc = __ballot_sync(0xffffffffu, fc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int within = __popc(ba & lt) | (__popc(bb & lt) << 10) | (__popc(bc & lt) << 20);
+    __syncthreads();
+    if (lane == 0) warp_sums[wid] = __popc(ba) | (__popc(bb) << 10) | (__popc(bc) << 20);
+    __syncthreads();
+    if (wid == 0) {
+        int v = lane < nw ? warp_sums[lane] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane < nw) warp_sums[lane] = inc - v;
+        if (lane == 31) warp_sums[32] = inc;
+    }
+    __syncthreads();
+    *total = warp_sums[32];
+    return warp_sums[wid] + within;
+}

@@ -37,7 +37,6 @@ struct K1Smem {                           /* 54.9 KB: four CTAs per SM */
     float sx[K1_XH * K1_XW], sy[K1_XH * K1_XW];
     float gx[3][K1_GH * K1_GW], gy[3][K1_GH * K1_GW];
     unsigned long long dil[5][K1_FH];     /* bit rows of the flag region (bit c = column c): depth-change pixels dilated by 0..4 columns */
-    unsigned zlo[K1_FH], zhi[K1_FH];      /* the undilated rows as the ballots deliver them: columns 0..31 and 32..39 */
     unsigned falo[K1_GH], fahi[K1_GH], fblo[K1_GH], fbhi[K1_GH];   /* finite dx / dy gradient elements per gradient row, same split */
     unsigned kmask[4][K1_TH];             /* per tile row: pixels whose smoothing window is 5, 4, 3, 2 */
     unsigned vmask[K1_TH], imask[K1_TH];  /* pixels that may get a normal (image border, finite z); pixels inside the image */
@@ -46,7 +45,7 @@ struct K1Smem {                           /* 54.9 KB: four CTAs per SM */
     unsigned short list2[K1_TH * K1_TW / 2];   /* windows of 3 and 2, tagged (pixel | k << 12); a tile with more takes them in place */
     int n5, n4, n32, pad;
 };
-static_assert(K1_FW <= 64 && K1_TW == 32, "bit rows: one 64-bit word per flag row, one warp lane per tile column");
+static_assert(K1_FW <= 64 && K1_TW == 32 && K1_FH % 4 == 0, "bit rows: one 64-bit word per flag row, one warp lane per tile column");
 static_assert(6 * K1_BAND * K1_GW * sizeof(double) <= (K1_RH * K1_RW + 2 * K1_XH * K1_XW) * sizeof(float), "column-sum band must fit in sz + sx + sy");
 static_assert(K1_TH % K1_BAND == 0 && 6 * K1_GW <= K1_THREADS, "one thread per (channel, gradient column)");
 
@@ -213,24 +212,28 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         if (lane == 0 && nvalid) atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
     }
 
-    /* S1: depth-change flags on the lateral coordinate z (reference quirk), halo 4, as bit rows: one warp per flag row for
-     * columns 0..31 (the ballot is the row), then the eight tail columns of four rows per warp */
-    for (int fr = wid; fr < K1_FH; fr += 8) {
-        const int se = (fr + 1) * K1_RW + lane + 1;
-        const float zc = s.sz[se];
-        const bool z0 = k1_bad_pair(zc, s.sz[se + 1]) || k1_bad_pair(s.sz[se - 1], zc) ||
-                        k1_bad_pair(zc, s.sz[se + K1_RW]) || k1_bad_pair(s.sz[se - K1_RW], zc);
-        const unsigned b = __ballot_sync(0xffffffffu, z0);
-        if (lane == 0) s.zlo[fr] = b;
-    }
+    /* S1 + S2: depth-change flags on the lateral coordinate z (reference quirk), halo 4, as bit rows, four flag rows per warp
+     * pass: columns 0..31 of each row (the ballot is the row), then the eight tail columns of the four rows in one go; lanes
+     * 0..3 then dilate "their" row: a flagged pixel within h columns, h = 0..4 (PCL's distance map along the row, capped at 5) */
     for (int q = wid; q < K1_FH / 4; q += 8) {
-        const int fr = q * 4 + (lane >> 3);
-        const int se = (fr + 1) * K1_RW + 32 + (lane & 7) + 1;
-        const float zc = s.sz[se];
-        const bool z0 = k1_bad_pair(zc, s.sz[se + 1]) || k1_bad_pair(s.sz[se - 1], zc) ||
-                        k1_bad_pair(zc, s.sz[se + K1_RW]) || k1_bad_pair(s.sz[se - K1_RW], zc);
-        const unsigned b = __ballot_sync(0xffffffffu, z0);
-        if ((lane & 7) == 0) s.zhi[fr] = (b >> (lane & 24)) & 255u;
+        unsigned long long m = 0ull;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int fr = q * 4 + (u < 4 ? u : (lane >> 3));
+            const int se = (fr + 1) * K1_RW + (u < 4 ? lane : 32 + (lane & 7)) + 1;
+            const float zc = s.sz[se];
+            const bool z0 = k1_bad_pair(zc, s.sz[se + 1]) || k1_bad_pair(s.sz[se - 1], zc) ||
+                            k1_bad_pair(zc, s.sz[se + K1_RW]) || k1_bad_pair(s.sz[se - K1_RW], zc);
+            const unsigned b = __ballot_sync(0xffffffffu, z0);
+            if (u < 4) { if (lane == u) m = b; }
+            else m |= (unsigned long long)((b >> (8 * (lane & 3))) & 255u) << 32;
+        }
+        if (lane < 4) {
+            const int fr = q * 4 + lane;
+            s.dil[0][fr] = m;
+#pragma unroll
+            for (int h = 1; h < 5; ++h) { m |= (m << 1) | (m >> 1); s.dil[h][fr] = m; }
+        }
     }
     /* S4 (independent of S1): gradient fields, halo 2, same row-aligned passes: columns 0..31 of a gradient row per warp, then
      * the four tail columns of eight rows per warp; the ballots are the rows of finite elements */
@@ -250,14 +253,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
         if (!tail) { if (lane == 0) { s.falo[rr] = ba; s.fblo[rr] = bb; } }
         else if ((lane & 3) == 0 && rr < K1_GH) { s.fahi[rr] = (ba >> (lane & 28)) & 15u; s.fbhi[rr] = (bb >> (lane & 28)) & 15u; }
-    }
-    __syncthreads();
-    /* S2: a flagged pixel within h columns, h = 0..4, for every flag row (PCL's distance map along the row, capped at 5) */
-    if (tid < K1_FH) {
-        unsigned long long m = (unsigned long long)s.zlo[tid] | ((unsigned long long)s.zhi[tid] << 32);
-        s.dil[0][tid] = m;
-#pragma unroll
-        for (int h = 1; h < 5; ++h) { m |= (m << 1) | (m >> 1); s.dil[h][tid] = m; }
     }
     __syncthreads();
     /* S3: smoothing size per owned pixel, one thread per tile row.  A flagged pixel at row distance a and column distance h
@@ -523,10 +518,10 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     for (int q = 0; q < 4; ++q) {
         const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
-        if (j >= N) break;
+        if (j >= M) break;
         unsigned char code = 0; int rep = -1;
-        const unsigned long long key = j < M ? key_at(j) : 0ull;
-        if (j < M && (j == 0 || key_at(j - 1) != key)) {
+        const unsigned long long key = key_at(j);
+        if (j == 0 || key_at(j - 1) != key) {
             float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
             for (int t = j; t < M && key_at(t) == key; ++t) { const float4 pw = P[vals[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
             const float fn = (float)n;
@@ -552,7 +547,7 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
                 }
             }
         }
-        d.rep[base + j] = rep; d.code[base + j] = code;
+        d.rep[base + j] = rep; d.code[base + j] = code;                       /* positions past M are never read */
     }
     c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
     c3 = __reduce_add_sync(0xffffffffu, c3); c4 = __reduce_add_sync(0xffffffffu, c4);
@@ -602,22 +597,21 @@ __global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
     __shared__ int wsum[33];
     const int f = blockIdx.y, N = d.N;
     const size_t base = (size_t)f * N;
+    const int M = d.foff[f + 1] - d.foff[f];                              /* sorted positions of this frame */
+    if (blockIdx.x * 1024 >= M) return;
     const int *blk = d.blk + ((size_t)f * d.nblk + blockIdx.x) * 5;
     int b_head = blk[0], b_h = blk[3], b_v = blk[4];
     for (int q = 0; q < 4; ++q) {
         const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
-        const unsigned char code = j < N ? d.code[base + j] : 0;
-        const int rep = j < N ? d.rep[base + j] : -1;
+        const unsigned char code = j < M ? d.code[base + j] : 0;
+        const int rep = j < M ? d.rep[base + j] : -1;
         int tot;
-        const int ph = sp_block_scan_flag((code & SPC_HEAD) != 0, wsum, &tot);
+        const int pk = sp_block_scan_flags3((code & SPC_HEAD) != 0, (code & SPC_H) != 0, (code & SPC_V) != 0, wsum, &tot);
+        const int ph = pk & 1023, pH = (pk >> 10) & 1023, pV = pk >> 20;
         if (code & SPC_HEAD) { d.voxel_idx[base + b_head + ph] = rep; d.voxel_code[base + b_head + ph] = code; }
-        b_head += tot;
-        const int pH = sp_block_scan_flag((code & SPC_H) != 0, wsum, &tot);
         if (code & SPC_H) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f) * N + b_h + pH] = pw; }
-        b_h += tot;
-        const int pV = sp_block_scan_flag((code & SPC_V) != 0, wsum, &tot);
         if (code & SPC_V) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f + 1) * N + b_v + pV] = pw; }
-        b_v += tot;
+        b_head += tot & 1023; b_h += (tot >> 10) & 1023; b_v += tot >> 20;
     }
 }
 
