@@ -369,7 +369,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     d.nblk = (int)((N + 1023) / 1024);
 #define DA(ptr, n) if ((e = dalloc(ctx, &(ptr), (n))) != cudaSuccess) return fail("cudaMalloc " #ptr, e)
     DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
-    DA(d.x, BN); DA(d.y, BN); DA(d.z, BN); DA(d.xyzw, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
+    DA(d.xyzw, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
     DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 2);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
@@ -661,11 +661,16 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
     CK(d2h(counts.data(), d.counts + f * SP_NCOUNT, sizeof(int) * SP_NCOUNT));
     auto put_i = [&](const std::vector<int> &v) { out.resize(v.size() * 4); if (!v.empty()) memcpy(out.data(), v.data(), out.size()); };
     if (name == "xyz" || name == "normals") {
-        std::vector<float> a(N), b(N), c(N);
-        const bool nrm = name == "normals";
-        CK(d2h(a.data(), (nrm ? d.nx : d.x) + f * N, N * 4)); CK(d2h(b.data(), (nrm ? d.ny : d.y) + f * N, N * 4)); CK(d2h(c.data(), (nrm ? d.nz : d.z) + f * N, N * 4));
         out.resize(N * 12);
         float *o = (float *)out.data();
+        if (name == "xyz") {
+            std::vector<float4> p(N);
+            CK(d2h(p.data(), d.xyzw + f * N, N * 16));
+            for (size_t i = 0; i < N; ++i) { o[3 * i] = p[i].x; o[3 * i + 1] = p[i].y; o[3 * i + 2] = p[i].z; }
+            return SP_OK;
+        }
+        std::vector<float> a(N), b(N), c(N);
+        CK(d2h(a.data(), d.nx + f * N, N * 4)); CK(d2h(b.data(), d.ny + f * N, N * 4)); CK(d2h(c.data(), d.nz + f * N, N * 4));
         for (size_t i = 0; i < N; ++i) { o[3 * i] = a[i]; o[3 * i + 1] = b[i]; o[3 * i + 2] = c[i]; }
         return SP_OK;
     }
@@ -793,10 +798,9 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
     if (n) CK(cudaMemcpy(idx.data(), d.plane_idx + f * N + r.planes[plane].first, (size_t)n * 4, cudaMemcpyDeviceToHost));
     if (pixel_idx && n) memcpy(pixel_idx, idx.data(), (size_t)n * 4);
     if (xyz && n) {
-        std::vector<float> a(N), b(N), c(N);
-        CK(cudaMemcpy(a.data(), d.x + f * N, N * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), d.y + f * N, N * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(c.data(), d.z + f * N, N * 4, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < n; ++i) { xyz[3 * i] = a[idx[i]]; xyz[3 * i + 1] = b[idx[i]]; xyz[3 * i + 2] = c[idx[i]]; }
+        std::vector<float4> p(N);
+        CK(cudaMemcpy(p.data(), d.xyzw + f * N, N * 16, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) { xyz[3 * i] = p[idx[i]].x; xyz[3 * i + 1] = p[idx[i]].y; xyz[3 * i + 2] = p[idx[i]].z; }
     }
     return n;
 }
@@ -812,12 +816,11 @@ struct DevicePoints : sp_stairmodel::StairPoints {
         const int n = fr->planes[plane].count;
         std::vector<int> idx((size_t)n);
         if (n && cudaMemcpy(idx.data(), d.plane_idx + f * N + fr->planes[plane].first, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
-        if (hx.empty()) {
-            hx.resize(N); hy.resize(N); hz.resize(N);
-            if (cudaMemcpy(hx.data(), d.x + f * N, N * 4, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(hy.data(), d.y + f * N, N * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
-                cudaMemcpy(hz.data(), d.z + f * N, N * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        if (hp.empty()) {
+            hp.resize(N);
+            if (cudaMemcpy(hp.data(), d.xyzw + f * N, N * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
         }
-        for (int i = 0; i < n; ++i) { xyz.push_back(hx[(size_t)idx[(size_t)i]]); xyz.push_back(hy[(size_t)idx[(size_t)i]]); xyz.push_back(hz[(size_t)idx[(size_t)i]]); }
+        for (int i = 0; i < n; ++i) { const float4 &p = hp[(size_t)idx[(size_t)i]]; xyz.push_back(p.x); xyz.push_back(p.y); xyz.push_back(p.z); }
         return true;
     }
     bool minmax(int plane, const float *c, const float *dir, float *max_xyz, float *min_xyz) override
@@ -834,12 +837,11 @@ struct DevicePoints : sp_stairmodel::StairPoints {
             if (ord[w] < 0) return false;
             int pix = -1;
             if (cudaMemcpy(&pix, d.plane_idx + f * N + pr.first + ord[w], 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
-            if (cudaMemcpy(xyz, d.x + f * N + pix, 4, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(xyz + 1, d.y + f * N + pix, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
-                cudaMemcpy(xyz + 2, d.z + f * N + pix, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+            if (cudaMemcpy(xyz, d.xyzw + f * N + pix, 12, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
         }
         return true;
     }
-    std::vector<float> hx, hy, hz;
+    std::vector<float4> hp;
 };
 } // namespace
 
@@ -912,7 +914,7 @@ int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, cons
         if (pixel) *pixel = pix;
         if (xyz) {
             xyz[0] = xyz[1] = xyz[2] = qnan;
-            if (pix >= 0) { CK(cudaMemcpy(xyz, d.x + f * N + pix, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(xyz + 1, d.y + f * N + pix, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(xyz + 2, d.z + f * N + pix, 4, cudaMemcpyDeviceToHost)); }
+            if (pix >= 0) CK(cudaMemcpy(xyz, d.xyzw + f * N + pix, 12, cudaMemcpyDeviceToHost));
         }
     }
     return SP_OK;

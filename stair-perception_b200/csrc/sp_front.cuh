@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
             bool crop = false;
             if (inside) {
                 const size_t gi = tile_base + (size_t)tr * W + lane;
-                d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz; d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
+                d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
                 if (sp_finite3(ox, oy, oz)) {
                     ++nvalid;
                     if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_ingest_plain(SpDev d, int *knn_mm)
         const unsigned rgba = __float_as_uint(p.w);
         if ((rgba & 255u) == 0u || ((rgba >> 8) & 255u) == 0u || ((rgba >> 16) & 255u) == 0u) { ox = oy = oz = qnan; }
         const size_t gi = (size_t)f * N + i;
-        d.x[gi] = ox; d.y[gi] = oy; d.z[gi] = oz; d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
+        d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
         d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan;
         bool crop = false;
         if (sp_finite3(ox, oy, oz)) {
@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) k_knn_key(SpDev d, const SpKnnGrid *grid)
     const float h = grid[f].h;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const size_t gi = (size_t)f * N + i;
-        const float x = d.x[gi], y = d.y[gi], z = d.z[gi];
+        const float4 pw = d.xyzw[gi];
+        const float x = pw.x, y = pw.y, z = pw.z;
         unsigned key = 0xFFFFFFFFu;
         if (sp_finite3(x, y, z)) { int a, b, c; sp_knn_cell(x, y, z, h, a, b, c); key = sp_knn_bucket(a, b, c); }
         d.key_a[gi] = ((unsigned long long)(unsigned)f << 32) | key;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(256) k_knn_starts(SpDev d, int *bstart, int *b
         const unsigned key = (unsigned)d.key_b[base + j];
         if (key == 0xFFFFFFFFu) continue;
         const unsigned pix = d.val_b[base + j];
-        kpts[base + j] = make_float4(d.x[base + pix], d.y[base + pix], d.z[base + pix], __int_as_float((int)pix));
+        { float4 pw = d.xyzw[base + pix]; pw.w = __int_as_float((int)pix); kpts[base + j] = pw; }
         if (j == 0 || (unsigned)d.key_b[base + j - 1] != key) { bs[key] = j; atomicAdd(&grid[f].occupied, 1); }
         if (j == N - 1 || (unsigned)d.key_b[base + j + 1] != key) be[key] = j + 1;
     }
@@ -337,7 +338,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
             const bool have = i < want && key != INF;
             if (have) {
                 const unsigned pix = (unsigned)key;
-                W.gx[i] = d.x[base + pix]; W.gy[i] = d.y[base + pix]; W.gz[i] = d.z[base + pix];
+                const float4 pw = d.xyzw[base + pix];
+                W.gx[i] = pw.x; W.gy[i] = pw.y; W.gz[i] = pw.z;
             }
             cnt += have ? 1 : 0;
         }

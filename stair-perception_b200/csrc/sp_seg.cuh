@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) k_merge(SpDev d, int nB)
     if (f >= nB) return;
     MgWarp &S = SW[wid];
     int rpos = 0;                                             /* warp-uniform position in the rand() stream */
-    const float *X = d.x + (size_t)f * d.N, *Y = d.y + (size_t)f * d.N, *Z = d.z + (size_t)f * d.N;
+    const float4 *PT = d.xyzw + (size_t)f * d.N;
     for (int hv = 0; hv < 2; ++hv) {
         const int s = 2 * f + hv;
         SpSegPlane *chunks = d.chunks + s * SP_PSEG;
@@ -665,7 +665,8 @@ __global__ void __launch_bounds__(MG_WARPS * 32) k_merge(SpDev d, int nB)
             if (lane < 20) {
                 const int r = d.rnd[(rpos + lane) & (SP_RAND_LEN - 1)];
                 const int pi = mg_point(d, s, chunks, nxt, mp[i].head, r % np);
-                S.sx[i][lane] = X[pi]; S.sy[i][lane] = Y[pi]; S.sz[i][lane] = Z[pi];
+                const float4 pw = PT[pi];
+                S.sx[i][lane] = pw.x; S.sy[i][lane] = pw.y; S.sz[i][lane] = pw.z;
             }
             rpos += 20;
             __syncwarp();
@@ -897,7 +898,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
     }
     __syncthreads();
     if (tid == 0) {
-        const float *X = d.x + (size_t)f * d.N, *Y = d.y + (size_t)f * d.N, *Z = d.z + (size_t)f * d.N;
+        const float4 *P = d.xyzw + (size_t)f * d.N;
         sp_plane_record r;
         r.type = (s & 1) ? 0 : 1; r.ptype = 3; r.count = n; r.first = 0;
         const float qnan = __int_as_float(0x7fc00000);
@@ -906,8 +907,8 @@ __global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
         for (int k = 0; k < 9; ++k) r.evec[k] = S.evs[k];
         for (int a2 = 0; a2 < 3; ++a2) {
             for (int k = 0; k < 3; ++k) { r.pt_min[a2][k] = qnan; r.pt_max[a2][k] = qnan; }
-            if (S.imn[a2] >= 0) { r.pt_min[a2][0] = X[S.imn[a2]]; r.pt_min[a2][1] = Y[S.imn[a2]]; r.pt_min[a2][2] = Z[S.imn[a2]]; }
-            if (S.imx[a2] >= 0) { r.pt_max[a2][0] = X[S.imx[a2]]; r.pt_max[a2][1] = Y[S.imx[a2]]; r.pt_max[a2][2] = Z[S.imx[a2]]; }
+            if (S.imn[a2] >= 0) { const float4 pw = P[S.imn[a2]]; r.pt_min[a2][0] = pw.x; r.pt_min[a2][1] = pw.y; r.pt_min[a2][2] = pw.z; }
+            if (S.imx[a2] >= 0) { const float4 pw = P[S.imx[a2]]; r.pt_max[a2][0] = pw.x; r.pt_max[a2][1] = pw.y; r.pt_max[a2][2] = pw.z; }
         }
         for (int k = 0; k < 3; ++k) r.pcenter[k] = (r.pt_max[0][k] + r.pt_min[0][k]) / 2;
         d.info[s * SP_PSEG + m] = r;
@@ -992,7 +993,8 @@ __global__ void __launch_bounds__(256) k_minmax_proj(SpDev d, int frame, int fir
     float bmx = -FLT_MAX, bmn = FLT_MAX; int amx = -1, amn = -1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int pix = idx[i];
-        const float px = d.x[base + pix] - cx, py = d.y[base + pix] - cy, pz = d.z[base + pix] - cz;
+        const float4 pw = d.xyzw[base + pix];
+        const float px = pw.x - cx, py = pw.y - cy, pz = pw.z - cz;
         const float proj = vx * px + (vy * py + vz * pz);            /* Eigen's unrolled 3-term reduction: c0 + (c1 + c2) */
         if (proj > bmx) { bmx = proj; amx = i; }
         if (proj < bmn) { bmn = proj; amn = i; }
