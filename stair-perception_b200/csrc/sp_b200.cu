@@ -369,7 +369,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     d.nblk = (int)((N + 1023) / 1024);
 #define DA(ptr, n) if ((e = dalloc(ctx, &(ptr), (n))) != cudaSuccess) return fail("cudaMalloc " #ptr, e)
     DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
-    DA(d.xyzw, BN); DA(d.nx, BN); DA(d.ny, BN); DA(d.nz, BN);
+    DA(d.xyzw, BN); DA(d.nrm, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
     DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 2);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
@@ -663,15 +663,9 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
     if (name == "xyz" || name == "normals") {
         out.resize(N * 12);
         float *o = (float *)out.data();
-        if (name == "xyz") {
-            std::vector<float4> p(N);
-            CK(d2h(p.data(), d.xyzw + f * N, N * 16));
-            for (size_t i = 0; i < N; ++i) { o[3 * i] = p[i].x; o[3 * i + 1] = p[i].y; o[3 * i + 2] = p[i].z; }
-            return SP_OK;
-        }
-        std::vector<float> a(N), b(N), c(N);
-        CK(d2h(a.data(), d.nx + f * N, N * 4)); CK(d2h(b.data(), d.ny + f * N, N * 4)); CK(d2h(c.data(), d.nz + f * N, N * 4));
-        for (size_t i = 0; i < N; ++i) { o[3 * i] = a[i]; o[3 * i + 1] = b[i]; o[3 * i + 2] = c[i]; }
+        std::vector<float4> p(N);
+        CK(d2h(p.data(), (name == "xyz" ? d.xyzw : d.nrm) + f * N, N * 16));
+        for (size_t i = 0; i < N; ++i) { o[3 * i] = p[i].x; o[3 * i + 1] = p[i].y; o[3 * i + 2] = p[i].z; }
         return SP_OK;
     }
     if (name == "counts") { put_i(counts); return SP_OK; }

@@ -3,7 +3,7 @@
  *
  * One context processes chunks of up to `B` independent frames of N = W*H points.  Everything a frame needs
  * lives in HBM in structure-of-arrays form, frame-major:
- *   xyzw, nx, ny, nz      [B][N]           levelled + masked points as float4 {x, y, z, 0}, normals as three float planes (pixel order)
+ *   xyzw, nrm             [B][N] float4    levelled + masked points {x, y, z, 0} and normals {nx, ny, nz, 0} (pixel order)
  *   key/val (x2)          [B*N]  u64/u32   (frame << 32 | voxel index) and pixel index, before/after the radix sort
  *   rep, code             [B][N]           per sorted position: voxel representative pixel and its class bits
  *   "segments"            s = 2*frame + {0: horizontal set, 1: vertical set}; every per-segment array has capacity N
@@ -76,7 +76,7 @@ struct SpDev {
     const float *R;            /* [B][9] or NULL */
     /* stage 1 */
     float4 *xyzw;              /* [B][N] levelled + masked points {x, y, z, 0} (pixel order): one 32-byte sector per gathered point */
-    float *nx, *ny, *nz;       /* [B][N] normals */
+    float4 *nrm;               /* [B][N] normals {nx, ny, nz, 0} */
     int *mm;                   /* [B][8] ordered-int min xyz, max xyz, + 2 pad */
     int *counts;               /* [B][SP_NCOUNT] */
     SpFrameGrid *grid;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void k1_finish(const SpDev &d, size_t gi, float px, f
         if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
         onx = fx; ony = fy; onz = fz;
     }
-    d.nx[gi] = onx; d.ny[gi] = ony; d.nz[gi] = onz;
+    d.nrm[gi] = make_float4(onx, ony, onz, 0.f);
 }
 
 /* k x k box sums of the two gradient fields around tile pixel e, in the oracle's order (rows top to bottom of row sums
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
     for (int it = 0; it < K1_TH / 8; ++it) {
         const int tr = it * 8 + wid, e = tr * K1_TW + lane;
         const unsigned k5 = s.kmask[0][tr], k4 = s.kmask[1][tr], k3 = s.kmask[2][tr], k2 = s.kmask[3][tr], bit = 1u << lane;
-        if (s.imask[tr] & ~(k5 | k4 | k3 | k2) & bit) { const size_t gi = tile_base + (size_t)tr * W + lane; d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan; }
+        if (s.imask[tr] & ~(k5 | k4 | k3 | k2) & bit) { const size_t gi = tile_base + (size_t)tr * W + lane; d.nrm[gi] = make_float4(qnan, qnan, qnan, 0.f); }
         if (k5 & bit) s.list[s.base[0][tr] + __popc(k5 & lt)] = (unsigned short)e;
         else if (k4 & bit) s.list[K1_TH * K1_TW - 1 - (s.base[1][tr] + __popc(k4 & lt))] = (unsigned short)e;
         else if ((k3 | k2) & bit) {
@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
                 if (best > dis) { best = dis; rep = (int)p; }
             }
             code = SPC_HEAD; ++c0;
-            const float nx = d.nx[base + rep], ny = d.ny[base + rep], nz = d.nz[base + rep];
+            const float4 nw = d.nrm[base + rep];
+            const float nx = nw.x, ny = nw.y, nz = nw.z;
             if (sp_finite3(nx, ny, nz)) {
                 code |= SPC_NONAN; ++c1;
                 const float4 pw = P[rep];

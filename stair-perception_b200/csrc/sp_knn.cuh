@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_ingest_plain(SpDev d, int *knn_mm)
         if ((rgba & 255u) == 0u || ((rgba >> 8) & 255u) == 0u || ((rgba >> 16) & 255u) == 0u) { ox = oy = oz = qnan; }
         const size_t gi = (size_t)f * N + i;
         d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
-        d.nx[gi] = qnan; d.ny[gi] = qnan; d.nz[gi] = qnan;
+        d.nrm[gi] = make_float4(qnan, qnan, qnan, 0.f);
         bool crop = false;
         if (sp_finite3(ox, oy, oz)) {
             ++nvalid;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
             const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
             const float cs = (vx * fx + vy * fy + vz * fz);
             if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
-            d.nx[base + qi] = fx; d.ny[base + qi] = fy; d.nz[base + qi] = fz;
+            d.nrm[base + qi] = make_float4(fx, fy, fz, 0.f);
         }
         __syncwarp();
     }
