@@ -267,13 +267,15 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_cl_scan");
         k_cl_scatter<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_scatter");
+        k_cl_runs<<<2 * nB, 1024, 0, st>>>(d);
+        mark(ctx, "k_cl_runs");
         k_cl_union<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_union");
         k_cl_flatten<<<dim3(seg_gx, 2 * nB), 256, 0, st>>>(d);
         mark(ctx, "k_cl_flatten");
         k_cl_rank<<<2 * nB, RK_THREADS, 0, st>>>(d);
         mark(ctx, "k_cl_rank");
-        ctx->launches += 6;
+        ctx->launches += 7;
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     if (want_seg) {

@@ -117,6 +117,47 @@ __device__ __forceinline__ void sp_uf_unite(int *parent, int a, int b)
     }
 }
 
+/* Runs: the segment's points are in voxel order, so list neighbours are mostly spatial neighbours (a tread is walked forward
+ * column by column, a riser downwards).  Consecutive points closer than the tolerance form a run, and a run is a ready-made
+ * depth-1 tree: parent = first position of the run (a prefix maximum over the run starts, one CTA per segment, no atomics).
+ * Every tree edge is an edge of the radius graph, so the components k_cl_union ends with are unchanged -- but it starts from a
+ * few hundred shallow trees per surface instead of one node per point, and its "same parent?" filter is exact inside a run. */
+__global__ void __launch_bounds__(1024) k_cl_runs(SpDev d)
+{
+    __shared__ int wmax[32];
+    __shared__ int carry;
+    const int s = blockIdx.x, n = d.seg_n[s];
+    const size_t base = (size_t)s * d.N;
+    const float4 *pts = d.pts + base;
+    int *parent = d.parent + base;
+    const float r2 = d.c.r2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        int head = 0;                                                    /* start of the run if this point starts one, else 0 */
+        if (i < n && i > 0) {
+            const float4 p = pts[i], q = pts[i - 1];
+            const float d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
+            float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
+            if (!(dist < r2)) head = i;
+        }
+        int inc = head;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, u); }
+        if (lane == 31) wmax[wid] = inc;
+        __syncthreads();
+        int pre = carry;
+        for (int w = 0; w < wid; ++w) pre = max(pre, wmax[w]);
+        inc = max(inc, pre);
+        if (i < n) parent[i] = inc;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = inc;
+        __syncthreads();
+    }
+}
+
 /* One thread per point in bucket-major order.  Every unordered pair of points in adjacent cells is tested exactly
  * once: own cell against members with a smaller list position, plus the 13 "forward" neighbour cells.  (Two cells
  * sharing a bucket only cause repeated, idempotent unions.)  Union-find is indexed by list position, so a

@@ -1,5 +1,5 @@
-"""Per-source-line instruction counts of one kernel from an .ncu-rep captured with --import-source on:
-python tools/ncu_lines.py report.ncu-rep [top=40]"""
+"""Per-source-line instruction counts, stall samples and shared-memory wavefronts from an .ncu-rep captured with
+--import-source on:  python tools/ncu_lines.py report.ncu-rep [top=40] [kernel-name substring]"""
 import csv
 import subprocess
 import sys
@@ -8,15 +8,18 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    want = sys.argv[3] if len(sys.argv) > 3 else ""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    out, hdr, fname = [], None, ""
+    out, hdr, fname, func = [], None, "", ""
     for r in rows:
         if len(r) >= 2 and r[0] == "File Path":
             fname = r[1].split("/")[-1]
+        elif len(r) >= 2 and r[0] == "Function Name":
+            func = r[1]
         elif len(r) > 8 and r[0] == "Line No":
             hdr = r
-        elif hdr and len(r) == len(hdr) and r[2] == "-":          # a source line row (its SASS rows carry an address)
+        elif hdr and len(r) == len(hdr) and r[2] == "-" and want in func:     # a source line row (its SASS rows carry an address)
             ci, ct, cn = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
             cw, cx = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Excessive")
             try:
