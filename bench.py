@@ -204,6 +204,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries ONE JSON line: everything libraries print there while the run lasts (NCCL's version banner, for one) goes to
+    # stderr instead; the descriptor is handed back just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
@@ -376,7 +382,10 @@ def main():
             "stage_ms_last_chunk": stage_full, "voxel_stage_ms": float(np.mean(vox_ms)),
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
