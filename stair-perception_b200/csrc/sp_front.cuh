@@ -98,8 +98,28 @@ __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e
         }
         sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
     }
-    const int sxe = (rr + 3) * K1_XW + cc + 3;
-    k1_finish(d, tile_base + (size_t)rr * W + cc, s.sx[sxe], s.sy[sxe], s.sz[(rr + K1_HALO) * K1_RW + cc + K1_HALO], sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
+    const size_t gi = tile_base + (size_t)rr * W + cc;
+    const float4 pw = d.xyzw[gi];                       /* the point itself, for the flip: written by this CTA in S0b, a barrier ago */
+    k1_finish(d, gi, pw.x, pw.y, pw.z, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
+}
+
+/* Exact path, first half: thread u < 6 * K1_GW = (channel, gradient column) slides a 5-row column sum down the K1_BAND tile rows
+ * from b0 on and leaves them in csum[channel][row][column] */
+__device__ __forceinline__ void k1_column_sums(const K1Smem &s, double *csum, int u, int b0)
+{
+    const int ch = u / K1_GW, col = u - ch * K1_GW;
+    if (ch >= 6) return;
+    const float *g = ch < 3 ? s.gx[ch] : s.gy[ch - 3];
+    float v[K1_BAND + 4];
+#pragma unroll
+    for (int a = 0; a < K1_BAND + 4; ++a) v[a] = g[(b0 + a) * K1_GW + col];
+    double w = (double)v[0] + (double)v[1] + (double)v[2] + (double)v[3];
+#pragma unroll
+    for (int i = 0; i < K1_BAND; ++i) {
+        w += (double)v[i + 4];
+        csum[(ch * K1_BAND + i) * K1_GW + col] = w;
+        w -= (double)v[i];
+    }
 }
 
 /* A coordinate that is NaN, zero, or 2^-21 <= |c| < 8 is a multiple of 2^-44 below 8.  If every coordinate of the tile is like
@@ -258,7 +278,11 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
     /* S3: smoothing size per owned pixel, one thread per tile row.  A flagged pixel at row distance a and column distance h
      * allows a window of kcat[a][h] (chamfer 1.0/1.4: d = 1.4*min + (max-min); d<=2 -> 0 (NaN), (2,3) -> 2, [3,4) -> 3, [4,5) -> 4,
      * >=5 -> 5):  a=0: 0 0 0 3 4 5 | a=1: 0 0 2 3 4 5 | a=2: 0 2 2 3 4 5 | a=3: 3 3 3 4 5 5 | a=4: 4 4 4 5 5 5  (h = 0..5).
-     * "window <= k" is therefore an OR of dilated rows; the list offsets of each row come from a warp scan of the counts. */
+     * "window <= k" is therefore an OR of dilated rows; the list offsets of each row come from a warp scan of the counts.
+     * Meanwhile warps 1..7 of an exact tile start on the separable sums of S5 (column sums of the first band): the coordinates
+     * in sz / sx / sy had their last readers before the barrier above, the band may overwrite them. */
+    double *csum = reinterpret_cast<double *>(k1_raw);                      /* [6][K1_BAND][K1_GW], over sz / sx / sy */
+    if (exact && tid >= 32) k1_column_sums(s, csum, tid - 32, 0);
     if (tid < K1_TH) {
         const int r = tid + 4;
         const unsigned long long (*D)[K1_FH] = s.dil;
@@ -312,40 +336,19 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         }
     }
     __syncthreads();
-    /* S5: box sums + normal, one pass per window size.  Windows of 4, 3, 2 (and of 5 in a tile without the exactness
-     * guarantee) take the direct sums ... */
+    /* S5: box sums + normal.  The windows of 5 of an exact tile take separable sums, K1_BAND tile rows at a time: a thread per
+     * (channel, gradient column) slides a 5-row column sum down the band in shared memory, then a thread per pixel adds five
+     * neighbouring column sums per channel: exact sums, the same bits as the ordered sums of k1_normal<5>.  Windows of 4, 3, 2
+     * (and of 5 in a tile without the exactness guarantee) take the ordered sums; they are handed out from the last thread
+     * downwards, to the threads the first band leaves idle. */
     const int n5 = s.n5, n4 = s.n4, n32 = min(s.n32, K1_TH * K1_TW / 2);
-    if (!exact) { for (int i = tid; i < n5; i += K1_THREADS) k1_normal<5>(s, d, s.list[i], tile_base, W); }
-    for (int i = tid; i < n4; i += K1_THREADS) k1_normal<4>(s, d, s.list[K1_TH * K1_TW - 1 - i], tile_base, W);
-    for (int i = tid; i < n32; i += K1_THREADS) {
-        const int code = s.list2[i];
-        if ((code >> 12) == 3) k1_normal<3>(s, d, code & 0xfff, tile_base, W);
-        else k1_normal<2>(s, d, code & 0xfff, tile_base, W);
-    }
-    if (!exact || n5 == 0) return;                                          /* CTA-uniform */
-    /* ... the windows of 5 of an exact tile take separable sums, K1_BAND tile rows at a time: a thread per (channel, gradient
-     * column) slides a 5-row column sum down the band (shared memory: the band re-uses sz / sx / sy, whose last readers were
-     * the direct sums above), then a thread per pixel adds five neighbouring column sums per channel.  Exact sums: same bits
-     * as the ordered sums of k1_normal<5>.  The point itself (for the flip) comes back from global memory. */
-    double *csum = reinterpret_cast<double *>(k1_raw);                      /* [6][K1_BAND][K1_GW] */
-    const int ch = tid / K1_GW, col = tid - ch * K1_GW;
-    const float *g = ch < 3 ? s.gx[ch] : s.gy[ch < 6 ? ch - 3 : 0];
-    for (int b0 = 0; b0 < K1_TH; b0 += K1_BAND) {
+    for (int b0 = 0; b0 < (exact ? (n5 ? K1_TH : K1_BAND) : 0); b0 += K1_BAND) {    /* CTA-uniform bounds */
         const int p0 = s.base[0][b0], p1 = b0 + K1_BAND < K1_TH ? s.base[0][b0 + K1_BAND] : n5;
-        __syncthreads();                                                    /* previous band read / direct sums done with sz, sx, sy */
-        if (p1 > p0 && ch < 6) {
-            float v[K1_BAND + 4];
-#pragma unroll
-            for (int a = 0; a < K1_BAND + 4; ++a) v[a] = g[(b0 + a) * K1_GW + col];
-            double w = (double)v[0] + (double)v[1] + (double)v[2] + (double)v[3];
-#pragma unroll
-            for (int i = 0; i < K1_BAND; ++i) {
-                w += (double)v[i + 4];
-                csum[(ch * K1_BAND + i) * K1_GW + col] = w;
-                w -= (double)v[i];
-            }
+        if (b0 > 0) {                                                       /* the first band's column sums are there already */
+            __syncthreads();
+            if (p1 > p0) k1_column_sums(s, csum, tid, b0);
+            __syncthreads();
         }
-        __syncthreads();
         for (int i = p0 + tid; i < p1; i += K1_THREADS) {
             const int e = s.list[i], rr = e / K1_TW, cc = e - rr * K1_TW;
             const double *c = csum + (rr - b0) * K1_GW + cc;
@@ -358,6 +361,23 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
             const size_t gi = tile_base + (size_t)rr * W + cc;
             const float4 pw = d.xyzw[gi];
             k1_finish(d, gi, pw.x, pw.y, pw.z, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
+        }
+        if (b0 == 0) {
+            for (int i = K1_THREADS - 1 - tid; i < n4; i += K1_THREADS) k1_normal<4>(s, d, s.list[K1_TH * K1_TW - 1 - i], tile_base, W);
+            for (int i = K1_THREADS - 1 - tid; i < n32; i += K1_THREADS) {
+                const int code = s.list2[i];
+                if ((code >> 12) == 3) k1_normal<3>(s, d, code & 0xfff, tile_base, W);
+                else k1_normal<2>(s, d, code & 0xfff, tile_base, W);
+            }
+        }
+    }
+    if (!exact) {
+        for (int i = tid; i < n5; i += K1_THREADS) k1_normal<5>(s, d, s.list[i], tile_base, W);
+        for (int i = tid; i < n4; i += K1_THREADS) k1_normal<4>(s, d, s.list[K1_TH * K1_TW - 1 - i], tile_base, W);
+        for (int i = tid; i < n32; i += K1_THREADS) {
+            const int code = s.list2[i];
+            if ((code >> 12) == 3) k1_normal<3>(s, d, code & 0xfff, tile_base, W);
+            else k1_normal<2>(s, d, code & 0xfff, tile_base, W);
         }
     }
 }
