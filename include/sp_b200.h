@@ -168,9 +168,16 @@ int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, cons
  * pulls its points).  Returns SP_OK and fills *out: has_stair (what process() returns, StairPerception.cpp:190), the list
  * nodes in order -- kind 0 = concave line, 1 = step with {height, depth, line.h, line.d} = the four columns of
  * printStairEstParam (:265-290) -- and the final Plane::Ptype of every hand-off plane.  plane_h / plane_v index the frame's
- * hand-off planes (-1 = merged ground plane, -2 = the virtual riser of a tread-to-tread pair).  Not restated: the two side
- * planes and computePlaneCounter (:2861-3075), which only feed the GUI's contour drawing. */
+ * hand-off planes (-1 = merged ground plane, -2 - k = virtual riser k of a tread-to-tread pair).
+ * When a stair is found the model goes on like process() does (:192-193): the two side ("slide") planes of stairModel's step 8
+ * (:2562-2612, a sequential if / else-if extreme scan over the stair planes' points along the section normal) and
+ * computePlaneCounter (:2861-3075): the four contour points of every plane of the stair (what the GUI draws with addPolygon,
+ * modules/gui/gui.cpp:326-330) as intersections of the step lines with the side planes.  contour_width = the reference's
+ * counter.width (0 = untouched, 2 = front edge only, 4 = closed); points the reference never writes stay (0, 0, 0) like PCL's
+ * default-constructed points.  A virtual riser has no cloud: its lower edge passes through (0, 0, 0) in the reference as well
+ * (findMinMaxProjPoint on an empty cloud). */
 #define SP_MAX_STAIR_NODES 64
+#define SP_MAX_VIRTUAL_PLANES 32
 typedef struct sp_stair_node {
     int32_t kind, count, plane_h, plane_v;
     float line_h, line_d, line_coeff[6];
@@ -180,7 +187,15 @@ typedef struct sp_stair {
     int32_t has_stair, n_steps, n_nodes;
     int32_t ptype[SP_MAX_PLANES];
     float vnormal[3], snormal[3];
+    int32_t n_virtual;
     sp_stair_node nodes[SP_MAX_STAIR_NODES];
+    float slide_left[4], slide_right[4];                     /* plane coefficients A, B, C, D */
+    float contour[SP_MAX_PLANES][4][3];                      /* per hand-off plane */
+    int32_t contour_width[SP_MAX_PLANES];
+    float ground_contour[4][3];                              /* the merged ground plane (plane index -1) */
+    int32_t ground_contour_width;
+    int32_t virtual_contour_width[SP_MAX_VIRTUAL_PLANES];
+    float virtual_contour[SP_MAX_VIRTUAL_PLANES][4][3];      /* virtual riser k (plane index -2 - k) */
 } sp_stair;
 int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out);
 

@@ -159,6 +159,21 @@ def minmax_proj(pl, v):
     return pl.xyz[int(np.argmax(proj))], pl.xyz[int(np.argmin(proj))]
 
 
+def cross_point(line, plane):
+    """crossPointOfLineAndPlane (:2828-2844): line = (x0, y0, z0, a, b, c), plane = (A, B, C, D)"""
+    l, q = np.asarray(line, F), np.asarray(plane, F)
+    t = F(F(-1) * F(F(F(F(q[0] * l[0]) + F(q[1] * l[1])) + F(q[2] * l[2])) + q[3]))
+    t = F(t / F(F(F(q[0] * l[3]) + F(q[1] * l[4])) + F(q[2] * l[5])))
+    return np.array([F(F(l[3] * t) + l[0]), F(F(l[4] * t) + l[1]), F(F(l[5] * t) + l[2])], F)
+
+
+def _extreme(pl, v):
+    """findMinMaxProjPoint on a plane that may have no cloud (a virtual riser): PCL's default points are (0, 0, 0)"""
+    if pl.xyz is None or len(pl.xyz) == 0:
+        return np.zeros(3, F), np.zeros(3, F)
+    return minmax_proj(pl, v)
+
+
 def stair_model(params, planes, xyz, plane_idx):
     with np.errstate(all="ignore"):
         return _stair_model(params, planes, xyz, plane_idx)
@@ -377,7 +392,7 @@ def _stair_model(params, planes, xyz, plane_idx):
         a, b = P[chain[ci]], P[chain[ci + 1]]
         if a.type == HORIZONTAL and b.type == VERTICAL:
             l = line_from_two_planes(a.coef, b.coef)
-            node = {"kind": 0, "line": l}
+            node = {"kind": 0, "line": l, "mh": a, "mv": b}
             if prev_step is not None:
                 prev_step["depth"] = abs(float(F(l["d"] - prev_step["line"]["d"])))
             out["nodes"].append(node)
@@ -385,7 +400,7 @@ def _stair_model(params, planes, xyz, plane_idx):
         elif a.type == VERTICAL and b.type == HORIZONTAL:
             l = line_from_two_planes(a.coef, b.coef)
             count += 1
-            node = {"kind": 1, "line": l, "count": count, "height": 0.0, "depth": 0.0}
+            node = {"kind": 1, "line": l, "count": count, "height": 0.0, "depth": 0.0, "mh": b, "mv": a}
             if prev_concave is not None:
                 node["height"] = abs(float(F(l["h"] - prev_concave["line"]["h"])))
             else:
@@ -401,17 +416,91 @@ def _stair_model(params, planes, xyz, plane_idx):
             v.coef = np.array([vn[0], vn[1], vn[2], F(F(F(-v.center[0] * vn[0]) - F(v.center[1] * vn[1])) - F(v.center[2] * vn[2]))], F)
             P.append(v)
             l1 = line_from_two_planes(a.coef, v.coef)
-            node = {"kind": 0, "line": l1}
+            node = {"kind": 0, "line": l1, "mh": a, "mv": v}
             if prev_step is not None:
                 prev_step["depth"] = abs(float(F(l1["d"] - prev_step["line"]["d"])))
             out["nodes"].append(node)
             l2 = line_from_two_planes(b.coef, v.coef)
             count += 1
-            st = {"kind": 1, "line": l2, "count": count, "height": 0.0, "depth": 0.0}
+            st = {"kind": 1, "line": l2, "count": count, "height": 0.0, "depth": 0.0, "mh": b, "mv": v}
             st["height"] = abs(float(F(l2["h"] - prev_concave["line"]["h"]))) if prev_concave is not None else abs(float(F(a.center[0] - b.center[0])))
             out["nodes"].append(st)
             prev_step = st
     publish()
     out["has_stair"] = count > 0
     out["steps"] = [(n["height"], n["depth"], float(n["line"]["h"]), float(n["line"]["d"])) for n in out["nodes"] if n["kind"] == 1]
+    if count == 0:
+        return out
+
+    # 8. the side planes (:2562-2612): sequential `if .. else if` extreme scan along the section normal over the stair planes
+    sn = _normalized(np.cross(vn.astype(np.float64), np.array([-1.0, 0.0, 0.0])).astype(F))
+    right_max, left_min, rmax, lmin = F(-FLT_MAX), F(FLT_MAX), np.zeros(3, F), np.zeros(3, F)
+    for idx in chain:
+        m = P[idx]
+        if m.ptype == PT_GROUND:
+            continue
+        c = (m.xyz - m.center).astype(F)
+        proj = (sn[0] * c[:, 0] + (sn[1] * c[:, 1] + sn[2] * c[:, 2])).astype(F)
+        for i in range(len(proj)):
+            if proj[i] > right_max:
+                right_max, rmax = proj[i], m.xyz[i]
+            elif proj[i] < left_min:
+                left_min, lmin = proj[i], m.xyz[i]
+    sl = np.array([sn[0], sn[1], sn[2], F(F(-1) * F(F(F(sn[0] * lmin[0]) + F(sn[1] * lmin[1])) + F(sn[2] * lmin[2])))], F)
+    sr = np.array([sn[0], sn[1], sn[2], F(F(-1) * F(F(F(sn[0] * rmax[0]) + F(sn[1] * rmax[1])) + F(sn[2] * rmax[2])))], F)
+    out["slide_left"], out["slide_right"] = sl, sr
+
+    # computePlaneCounter (:2861-3075)
+    for m in P:
+        m.contour, m.cwidth = np.zeros((4, 3), F), 0
+    nodes = out["nodes"]
+    for ni, nd in enumerate(nodes):
+        last = ni == len(nodes) - 1
+        ln = np.asarray(nd["line"]["coeff"], F)
+        mh, mv = nd["mh"], nd["mv"]
+        with_dir = lambda pt: np.concatenate([np.asarray(pt, F), ln[3:6]])
+        if nd["kind"] == 1:
+            if mv.cwidth == 0:
+                pmax, _ = _extreme(mv, [1, 0, 0])
+                ld = with_dir(pmax)
+                mv.contour[0], mv.contour[1], mv.contour[2], mv.contour[3] = cross_point(ld, sl), cross_point(ld, sr), cross_point(ln, sr), cross_point(ln, sl)
+                mv.cwidth = 4
+            elif mv.cwidth == 2:
+                mv.contour[2], mv.contour[3] = cross_point(ln, sr), cross_point(ln, sl)
+                mv.cwidth = 4
+            if mh.cwidth == 0:
+                mh.contour[0], mh.contour[1] = cross_point(ln, sl), cross_point(ln, sr)
+                mh.cwidth = 2
+                if last:
+                    pmax, _ = _extreme(mh, vn)
+                    lb = with_dir(pmax)
+                    mh.contour[2], mh.contour[3] = cross_point(lb, sr), cross_point(lb, sl)
+                    mh.cwidth = 4
+        else:
+            if mh.cwidth == 0:
+                _, pmin = _extreme(mh, vn)
+                lf = with_dir(pmin)
+                mh.contour[0], mh.contour[1], mh.contour[2], mh.contour[3] = cross_point(lf, sl), cross_point(lf, sr), cross_point(ln, sr), cross_point(ln, sl)
+                mh.cwidth = 4
+            elif mh.cwidth == 2:
+                mh.contour[2], mh.contour[3] = cross_point(ln, sr), cross_point(ln, sl)
+                mh.cwidth = 4
+            if mv.cwidth == 0:
+                mv.contour[0], mv.contour[1] = cross_point(ln, sl), cross_point(ln, sr)
+                mv.cwidth = 2
+                if last:
+                    _, pmin = _extreme(mv, [1, 0, 0])
+                    lu = with_dir(pmin)
+                    mv.contour[2], mv.contour[3] = cross_point(lu, sr), cross_point(lu, sl)
+                    mv.cwidth = 4
+    out["contour"] = {}          # hand-off plane index -> (width, 4 x 3); -1 = merged ground plane; -2 - k = virtual riser k
+    vk = 0
+    for m in P:
+        if len(m.src) == 1:
+            out["contour"][m.src[0]] = (m.cwidth, m.contour)
+        elif len(m.src) > 1:
+            out["contour"][-1] = (m.cwidth, m.contour)
+        else:
+            out["contour"][-2 - vk] = (m.cwidth, m.contour)
+            vk += 1
     return out

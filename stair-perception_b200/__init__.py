@@ -111,8 +111,14 @@ def _ptr(a):
 
 STAIR_NODE_DTYPE = np.dtype([("kind", "<i4"), ("count", "<i4"), ("plane_h", "<i4"), ("plane_v", "<i4"), ("line_h", "<f4"), ("line_d", "<f4"),
                              ("line_coeff", "<f4", (6,)), ("height", "<f8"), ("depth", "<f8")])
+SP_MAX_VIRTUAL_PLANES = 32
 STAIR_DTYPE = np.dtype([("has_stair", "<i4"), ("n_steps", "<i4"), ("n_nodes", "<i4"), ("ptype", "<i4", (SP_MAX_PLANES,)), ("vnormal", "<f4", (3,)),
-                        ("snormal", "<f4", (3,)), ("pad", "<i4"), ("nodes", STAIR_NODE_DTYPE, (64,))])
+                        ("snormal", "<f4", (3,)), ("n_virtual", "<i4"), ("nodes", STAIR_NODE_DTYPE, (64,)),
+                        ("slide_left", "<f4", (4,)), ("slide_right", "<f4", (4,)),
+                        ("contour", "<f4", (SP_MAX_PLANES, 4, 3)), ("contour_width", "<i4", (SP_MAX_PLANES,)),
+                        ("ground_contour", "<f4", (4, 3)), ("ground_contour_width", "<i4"),
+                        ("virtual_contour_width", "<i4", (SP_MAX_VIRTUAL_PLANES,)), ("virtual_contour", "<f4", (SP_MAX_VIRTUAL_PLANES, 4, 3)),
+                        ("pad", "<i4")])
 
 
 class ResultDef(C.Structure):

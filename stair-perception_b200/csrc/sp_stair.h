@@ -4,7 +4,8 @@
  * minDistaceOfTwoCloud (:1503-1613).  Host code, as in the reference (it works on a few tens of planes); the only things
  * it needs from the planes' point clouds come through StairPoints: findMinMaxProjPoint (:2780-2808) as an on-device
  * reduction, and the concatenated cloud of a merged ground plane (:1748-1794), fetched only when two ground planes exist.
- * Not restated: the two side ("slide") planes (:2567-2615) and computePlaneCounter (:2861-3075), which only feed the GUI.
+ * When a stair is found: the two side ("slide") planes of step 8 (:2562-2612) and computePlaneCounter (:2861-3075), the contour
+ * of every plane of the stair that the GUI draws.
  *
  * The reference's quirks are kept on purpose (SURVEY.md section 8a "other behaviours", Appendix B):
  *   - ground detection reads the extents of vector_plane_sorted[i] with the HEIGHT-LIST index i (:1720-1721) and stores that
@@ -133,6 +134,15 @@ inline bool minmax_model_plane(StairPoints &pts, const MPlane &pl, const float *
         any = true;
     }
     return any;
+}
+
+/* crossPointOfLineAndPlane, :2828-2844: line {x0, y0, z0, a, b, c}, plane {A, B, C, D} */
+inline void cross_point(const float *l, const float *pl, float *pc)
+{
+    const float A = pl[0], B = pl[1], C = pl[2], D = pl[3];
+    float t = -1 * (A * l[0] + B * l[1] + C * l[2] + D);
+    t = t / (A * l[3] + B * l[4] + C * l[5]);
+    pc[0] = l[3] * t + l[0]; pc[1] = l[4] * t + l[1]; pc[2] = l[5] * t + l[2];
 }
 
 struct DirCount { V3 dir; int count; };
@@ -365,14 +375,17 @@ inline bool stair_model(const sp_params &prm, const sp_frame_result &fr, StairPo
     vn = normalized(vn);
     if (dot3(mcv[0].dir, vn) < 0) vn = v3(-vn.x, -vn.y, -vn.z);
     out->vnormal[0] = vn.x; out->vnormal[1] = vn.y; out->vnormal[2] = vn.z;
-    {   /* ---- 8. section normal (:2567-2570); the slide planes themselves are GUI-only and not restated ---- */
-        const V3 sn = normalized(v3(vn.y * 0 - vn.z * 0, vn.z * -1 - vn.x * 0, vn.x * 0 - vn.y * -1));     /* vnormal.cross((-1,0,0)) */
-        out->snormal[0] = sn.x; out->snormal[1] = sn.y; out->snormal[2] = sn.z;
-    }
+    /* ---- 8. section normal (:2567-2570); the slide planes follow below, once a stair is known to exist ---- */
+    const V3 sn = normalized(v3(vn.y * 0 - vn.z * 0, vn.z * -1 - vn.x * 0, vn.x * 0 - vn.y * -1));         /* vnormal.cross((-1,0,0)) */
+    out->snormal[0] = sn.x; out->snormal[1] = sn.y; out->snormal[2] = sn.z;
 
     /* ---- 9. modelling (:2622-2767) ---- */
     int count = 0, prev_concave = -1, prev_step = -1;
-    auto push = [&](const sp_stair_node &n) { if (out->n_nodes < SP_MAX_STAIR_NODES) out->nodes[out->n_nodes++] = n; return out->n_nodes - 1; };
+    std::vector<int> node_mh, node_mv;                         /* model plane (index into P) behind plane_h / plane_v of every node */
+    auto push = [&](const sp_stair_node &n, int mh, int mv) {
+        if (out->n_nodes < SP_MAX_STAIR_NODES) { out->nodes[out->n_nodes++] = n; node_mh.push_back(mh); node_mv.push_back(mv); }
+        return out->n_nodes - 1;
+    };
     auto src_of = [&](int model_plane) { return (P[(size_t)model_plane].src.size() == 1) ? P[(size_t)model_plane].src[0] : -1; };
     for (size_t ci = 0; ci + 1 < chain.size(); ++ci) {
         const int index = chain[ci], index_next = chain[ci + 1];
@@ -382,7 +395,7 @@ inline bool stair_model(const sp_params &prm, const sp_frame_result &fr, StairPo
             const Line l = line_from_two_planes(a.coef, b.coef);
             n.kind = 0; n.plane_h = src_of(index); n.plane_v = src_of(index_next); n.line_h = l.h; n.line_d = l.d; memcpy(n.line_coeff, l.coeff, 24);
             if (prev_step >= 0) out->nodes[prev_step].depth = fabs((double)(l.d - out->nodes[prev_step].line_d));
-            prev_concave = push(n);
+            prev_concave = push(n, index, index_next);
         } else if (a.type == TY_VERTICAL && b.type == TY_HORIZONTAL) {
             const Line l = line_from_two_planes(a.coef, b.coef);
             n.kind = 1; n.plane_v = src_of(index); n.plane_h = src_of(index_next); n.line_h = l.h; n.line_d = l.d; memcpy(n.line_coeff, l.coeff, 24);
@@ -393,7 +406,7 @@ inline bool stair_model(const sp_params &prm, const sp_frame_result &fr, StairPo
                 minmax_model_plane(pts, a, dir, pmax, pmin);
                 n.height = fabs((double)(pmax[0] - l.h));
             }
-            prev_step = push(n);
+            prev_step = push(n, index_next, index);
         } else if (a.type == TY_HORIZONTAL && b.type == TY_HORIZONTAL) {
             const float dir[3] = { vn.x, vn.y, vn.z };
             float h0[3] = { 0, 0, 0 }, h1[3] = { 0, 0, 0 }, tmp[3];
@@ -406,23 +419,118 @@ inline bool stair_model(const sp_params &prm, const sp_frame_result &fr, StairPo
             v.coef[3] = -v.center[0] * vn.x - v.center[1] * vn.y - v.center[2] * vn.z;
             memcpy(v.pt_min[1], h0, 12); memcpy(v.pt_max[1], h1, 12);
             P.push_back(v);
+            const int vidx = (int)P.size() - 1, vk = out->n_virtual < SP_MAX_VIRTUAL_PLANES ? out->n_virtual++ : SP_MAX_VIRTUAL_PLANES - 1;
             const Line l1 = line_from_two_planes(a.coef, v.coef);
-            n.kind = 0; n.plane_h = src_of(index); n.plane_v = -2; n.line_h = l1.h; n.line_d = l1.d; memcpy(n.line_coeff, l1.coeff, 24);
+            n.kind = 0; n.plane_h = src_of(index); n.plane_v = -2 - vk; n.line_h = l1.h; n.line_d = l1.d; memcpy(n.line_coeff, l1.coeff, 24);
             if (prev_step >= 0) out->nodes[prev_step].depth = fabs((double)(l1.d - out->nodes[prev_step].line_d));
-            push(n);                                           /* (prev_concave_line is not updated here in the reference, :2740) */
+            push(n, index, vidx);                              /* (prev_concave_line is not updated here in the reference, :2740) */
             const Line l2 = line_from_two_planes(b.coef, v.coef);
             sp_stair_node s; memset(&s, 0, sizeof(s));
-            s.kind = 1; s.plane_v = -2; s.plane_h = src_of(index_next); s.line_h = l2.h; s.line_d = l2.d; memcpy(s.line_coeff, l2.coeff, 24);
+            s.kind = 1; s.plane_v = -2 - vk; s.plane_h = src_of(index_next); s.line_h = l2.h; s.line_d = l2.d; memcpy(s.line_coeff, l2.coeff, 24);
             s.count = ++count;
             if (prev_concave >= 0) s.height = fabs((double)(l2.h - out->nodes[prev_concave].line_h));
             else s.height = fabs((double)(a.center[0] - b.center[0]));
-            prev_step = push(s);
+            prev_step = push(s, index_next, vidx);
         }
     }
     publish_ptypes();
     out->n_steps = count;
     out->has_stair = count > 0 ? 1 : 0;
-    return count > 0;
+    if (count == 0) return false;
+
+    /* ---- 8 (continued). the two side planes (:2571-2612): one sequential scan over the points of every non-ground plane of the
+     * chain, projections about each plane's own centre, `if (max) ... else if (min)` as in the reference.  (The reference runs
+     * it before step 9 whether or not a stair comes out; its only reader is computePlaneCounter, which needs a stair.) ---- */
+    float right_max = -FLT_MAX, left_min = FLT_MAX, rmax[3] = { 0, 0, 0 }, lmin[3] = { 0, 0, 0 };
+    std::vector<float> xyz;
+    for (int idx : chain) {
+        const MPlane &pl = P[(size_t)idx];
+        if (pl.ptype == PT_GROUND) continue;                       /* (step 9 does not touch ptype) */
+        xyz.clear();
+        for (int sidx : pl.src) pts.gather(sidx, xyz);
+        for (size_t i = 0; i + 2 < xyz.size(); i += 3) {
+            const V3 vp = v3(xyz[i] - pl.center[0], xyz[i + 1] - pl.center[1], xyz[i + 2] - pl.center[2]);
+            const float proj = dot3(sn, vp);
+            if (proj > right_max) { right_max = proj; memcpy(rmax, &xyz[i], 12); }
+            else if (proj < left_min) { left_min = proj; memcpy(lmin, &xyz[i], 12); }
+        }
+    }
+    float sl[4] = { sn.x, sn.y, sn.z, -1 * (sn.x * lmin[0] + sn.y * lmin[1] + sn.z * lmin[2]) };
+    float sr[4] = { sn.x, sn.y, sn.z, -1 * (sn.x * rmax[0] + sn.y * rmax[1] + sn.z * rmax[2]) };
+    memcpy(out->slide_left, sl, 16); memcpy(out->slide_right, sr, 16);
+
+    /* ---- computePlaneCounter (:2861-3075): walk the list; every plane collects its four contour points ---- */
+    struct Contour { float p[4][3]; int width; };
+    std::vector<Contour> C(P.size());
+    for (Contour &c : C) { memset(c.p, 0, sizeof(c.p)); c.width = 0; }
+    const float xdir[3] = { 1, 0, 0 }, vdir[3] = { vn.x, vn.y, vn.z };
+    for (int ni = 0; ni < out->n_nodes; ++ni) {
+        const sp_stair_node &nd = out->nodes[ni];
+        const bool last = ni == out->n_nodes - 1;
+        const float *ln = nd.line_coeff;
+        Contour &cv = C[(size_t)node_mv[(size_t)ni]], &ch = C[(size_t)node_mh[(size_t)ni]];
+        const MPlane &pv = P[(size_t)node_mv[(size_t)ni]], &ph = P[(size_t)node_mh[(size_t)ni]];
+        if (nd.kind == 1) {                                                   /* step: riser below, tread behind the line */
+            if (cv.width == 0) {
+                float mx[3] = { 0, 0, 0 }, mn[3] = { 0, 0, 0 };              /* lower edge: through the lowest point of the riser */
+                minmax_model_plane(pts, pv, xdir, mx, mn);
+                const float ld[6] = { mx[0], mx[1], mx[2], ln[3], ln[4], ln[5] };
+                cross_point(ld, sl, cv.p[0]); cross_point(ld, sr, cv.p[1]);
+                cross_point(ln, sr, cv.p[2]); cross_point(ln, sl, cv.p[3]);
+                cv.width = 4;
+            } else if (cv.width == 2) {
+                cross_point(ln, sr, cv.p[2]); cross_point(ln, sl, cv.p[3]);
+                cv.width = 4;
+            }
+            if (ch.width == 0) {
+                cross_point(ln, sl, ch.p[0]); cross_point(ln, sr, ch.p[1]);
+                ch.width = 2;
+                if (last) {                                                   /* back edge: through the farthest point of the tread */
+                    float mx[3] = { 0, 0, 0 }, mn[3] = { 0, 0, 0 };
+                    minmax_model_plane(pts, ph, vdir, mx, mn);
+                    const float lb[6] = { mx[0], mx[1], mx[2], ln[3], ln[4], ln[5] };
+                    cross_point(lb, sr, ch.p[2]); cross_point(lb, sl, ch.p[3]);
+                    ch.width = 4;
+                }
+            }
+        } else {                                                              /* concave line: tread in front, riser above */
+            if (ch.width == 0) {
+                float mx[3] = { 0, 0, 0 }, mn[3] = { 0, 0, 0 };              /* front edge: through the nearest point of the tread */
+                minmax_model_plane(pts, ph, vdir, mx, mn);
+                const float lf[6] = { mn[0], mn[1], mn[2], ln[3], ln[4], ln[5] };
+                cross_point(lf, sl, ch.p[0]); cross_point(lf, sr, ch.p[1]);
+                cross_point(ln, sr, ch.p[2]); cross_point(ln, sl, ch.p[3]);
+                ch.width = 4;
+            } else if (ch.width == 2) {
+                cross_point(ln, sr, ch.p[2]); cross_point(ln, sl, ch.p[3]);
+                ch.width = 4;
+            }
+            if (cv.width == 0) {
+                cross_point(ln, sl, cv.p[0]); cross_point(ln, sr, cv.p[1]);
+                cv.width = 2;
+                if (last) {                                                   /* upper edge: through the highest point of the riser */
+                    float mx[3] = { 0, 0, 0 }, mn[3] = { 0, 0, 0 };
+                    minmax_model_plane(pts, pv, xdir, mx, mn);
+                    const float lu[6] = { mn[0], mn[1], mn[2], ln[3], ln[4], ln[5] };
+                    cross_point(lu, sr, cv.p[2]); cross_point(lu, sl, cv.p[3]);
+                    cv.width = 4;
+                }
+            }
+        }
+    }
+    {
+        int vk = 0;
+        for (size_t i = 0; i < P.size(); ++i) {
+            if (P[i].src.size() == 1 && P[i].src[0] >= 0 && P[i].src[0] < SP_MAX_PLANES) {
+                memcpy(out->contour[P[i].src[0]], C[i].p, sizeof(C[i].p)); out->contour_width[P[i].src[0]] = C[i].width;
+            } else if (P[i].src.size() > 1) {
+                memcpy(out->ground_contour, C[i].p, sizeof(C[i].p)); out->ground_contour_width = C[i].width;
+            } else if (P[i].src.empty() && vk < SP_MAX_VIRTUAL_PLANES) {
+                memcpy(out->virtual_contour[vk], C[i].p, sizeof(C[i].p)); out->virtual_contour_width[vk] = C[i].width; ++vk;
+            }
+        }
+    }
+    return true;
 }
 
 }  // namespace sp_stairmodel

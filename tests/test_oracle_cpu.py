@@ -275,6 +275,33 @@ def test_stair_model_reproduces_published_step_table(sp, oracles):
     assert res0["has_stair"] and len(res0["steps"]) == 2
 
 
+def test_stair_contours_are_consistent(sp, oracles):
+    """computePlaneCounter (StairPerception.cpp:2861-3075) restated in the oracle: every closed contour of samples/0001 has its
+    corners 0 / 3 on the left side plane and 1 / 2 on the right one, all four within the RANSAC threshold of its own plane, and
+    the two side planes are parallel and about one stair width apart."""
+    from oracle import stair_model as sm
+    o = oracles["0001"]
+    planes = o.tap("planes")
+    res = sm.stair_model(sp.DEFAULT_PARAMS, planes, o.tap("xyz"), o.tap("plane_idx"))
+    sl, sr = res["slide_left"].astype(np.float64), res["slide_right"].astype(np.float64)
+    assert np.allclose(sl[:3], sr[:3]) and abs(np.linalg.norm(sl[:3]) - 1) < 1e-5
+    width = abs(sl[3] - sr[3])
+    assert 0.5 < width < 2.0, width
+    closed = 0
+    for k, (w, pts) in res["contour"].items():
+        if w != 4:
+            continue
+        closed += 1
+        p = pts.astype(np.float64)
+        for c, side in ((0, sl), (3, sl), (1, sr), (2, sr)):
+            assert abs(p[c] @ side[:3] + side[3]) < 1e-4, (k, c)
+        if k >= 0:
+            coef = planes[k]["coef"].astype(np.float64)
+            assert np.abs(p @ coef[:3] + coef[3]).max() < 0.03, (k, np.abs(p @ coef[:3] + coef[3]))
+            assert abs(np.linalg.norm(p[1] - p[0]) - width) < 0.02 and abs(np.linalg.norm(p[2] - p[3]) - width) < 0.02
+    assert closed >= 7                                   # four treads' risers + treads of a four-step stair (the ground may stay open)
+
+
 def test_stair_model_on_synthetic_ground_truth(sp, orc, synth):
     """synthetic frames have a known staircase: rise 0.11 m, run 0.28 m"""
     from oracle import stair_model as sm

@@ -287,6 +287,19 @@ def test_stair_model_matches_oracle_and_published_table(sp, orc, synth, samples,
         assert bool(st["has_stair"]) == bool(want["has_stair"]) and len(got) == len(want["steps"])
         assert np.allclose(np.array(got), np.array(want["steps"]), rtol=0, atol=2e-6), (got, want["steps"])
         assert list(st["ptype"][:int(res["n_planes"])]) == want["ptype"]
+        if want["has_stair"]:
+            # the side planes of step 8 and computePlaneCounter's contour of every plane (what the GUI draws)
+            assert np.allclose(st["slide_left"], want["slide_left"], rtol=0, atol=1e-5) and np.allclose(st["slide_right"], want["slide_right"], rtol=0, atol=1e-5)
+            assert int(st["n_virtual"]) == sum(1 for k in want["contour"] if k <= -2)
+            closed = 0
+            for k, (w, pts) in want["contour"].items():
+                gw, gp = ((st["contour_width"][k], st["contour"][k]) if k >= 0 else
+                          (st["ground_contour_width"], st["ground_contour"]) if k == -1 else
+                          (st["virtual_contour_width"][-2 - k], st["virtual_contour"][-2 - k]))
+                assert int(gw) == w, (k, int(gw), w)
+                assert np.allclose(gp, pts, rtol=0, atol=2e-5), (k, gp, pts)
+                closed += w == 4
+            assert closed >= 2 * len(want["steps"]) - 1
     res = ctx1.process_frames(samples["0001"][0])[0]
     got = np.array(sp.stair_steps(ctx1.stair_model(0)))
     published = np.array([(0.110046, 0.280456, 0.490394, 0.526096), (0.110491, 0.276792, 0.397571, 0.807455),
