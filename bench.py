@@ -155,8 +155,26 @@ def cpu_baseline(sp, recs, Rs, seconds_budget=12.0):
         orc.process_batch(sp.DEFAULT_PARAMS, recs, W, H, Rs, nthreads=nthreads)
         frames += n
     dt = time.perf_counter() - t0
+    # the reference's live path is single-threaded (one frame at a time; its screenshots show 137 ms per frame): latency of the
+    # same oracle on ONE core, per stage, over a few frames
+    single = {}
+    try:
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        per = []
+        for i in range(min(4, n)):
+            t1 = time.perf_counter()
+            o.process(recs[i], W, H, Rs[i], keep_taps=False)
+            per.append((time.perf_counter() - t1) * 1e3)
+            st = o.stage_ms()
+            for k, v in st.items():
+                single[k] = single.get(k, 0.0) + v / min(4, n)
+        o.close()
+        single = {"ms_per_frame": float(np.mean(per)), "frames": len(per), "stage_ms": {k: round(v, 3) for k, v in single.items()}}
+    except Exception as e:                                   # the throughput figure above stands on its own
+        single = {"error": str(e)}
     return {"value": frames / dt, "unit": "frames/s", "cores": nthreads, "kind": "port",
-            "sample": "%d synthetic 512x424 stair frames x %d passes, oracle/liborc.so, one frame per thread, %d threads" % (n, reps, nthreads)}
+            "sample": "%d synthetic 512x424 stair frames x %d passes, oracle/liborc.so, one frame per thread, %d threads" % (n, reps, nthreads),
+            "single_core": single}
 
 
 def run_reference(args):
@@ -321,6 +339,16 @@ def main():
     trace = ctx.trace_ms()
     ctx.set_trace(False)
     chunk_ms = sum(t for _, t in trace)
+    # the voxel stage's streaming kernel: reads every levelled point (16 B), writes (key, pixel) = 8 B per cropped point
+    tdict = dict(trace)
+    n_crop = int(results[:nb]["n_crop"].sum())
+    vk_bytes = 16 * N * nb + 8 * n_crop
+    vk_ms = tdict.get("k_voxel_key", 0.0)
+    roof_voxel = None
+    if vk_ms > 0:
+        roof_voxel = {"bound": "hbm", "kernel": "k_voxel_key", "achieved": vk_bytes / (vk_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": vk_bytes / (vk_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vk_ms, "algorithmic_bytes_per_launch": vk_bytes,
+                      "note": "timed inside a traced chunk (one CUDA event before and after the launch on the library's stream)"}
     kernels = [{"kernel": k, "ms": round(t, 4), "share": round(t / max(chunk_ms, 1e-9), 4)} for k, t in sorted(trace, key=lambda kv: -kv[1])[:8]]
 
     for _ in range(3):
@@ -376,6 +404,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_ingest_normals", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic("k_ingest_normals", nb), "peak_source": peak_src, "ms_per_launch": k1, "frames_per_launch": nb,
                          "algorithmic_bytes_per_launch": K1K2_BYTES_PER_POINT * N * nb},
+            "roofline_voxel_key": roof_voxel,
             "kernels_of_a_chunk": {"frames": nb, "ms": round(chunk_ms, 4), "top": kernels,
                                    "note": "k_cl_union (radius-graph union-find) and k_ransac are issue / latency bound on a few MB per chunk: no HBM roofline applies; "
                                            "k_ingest_normals is the largest kernel that streams the whole input"},
