@@ -132,11 +132,19 @@ struct sp_ctx {
     int64_t launches = 0;
     std::string err;
     std::mutex mu;
+    /* second lane: batches of two or more chunks alternate between this context and a twin (own workspace, own stream), so that
+     * the issue- and latency-bound tail of one chunk (clustering, RANSAC, plane statistics) shares the SMs with the streaming
+     * head of the next.  The twin is created on first use and shares the input staging buffers of its owner. */
+    sp_ctx *twin = nullptr, *owner = nullptr;
+    sp_ctx *last = nullptr;                   /* the lane that ran the last chunk: taps, stair model, stage times read it */
+    bool no_twin = false;                     /* SP_NO_TWIN=1 */
 };
 
 namespace {
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SP_ERR_CUDA; } } while (0)
+#define ERR(c) ((c)->owner ? (c)->owner->err : (c)->err)      /* a twin reports through its owner */
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ERR(ctx) = std::string(#call) + ": " + cudaGetErrorString(e_); return SP_ERR_CUDA; } } while (0)
+inline sp_ctx *lane_of_last_chunk(sp_ctx *ctx) { return ctx->last ? ctx->last : ctx; }
 
 template <class T> cudaError_t dalloc(sp_ctx *ctx, T **p, size_t n)
 {
@@ -330,13 +338,14 @@ int sp_set_params(sp_ctx *ctx, const sp_params *params)
     if (!ctx || !params) return SP_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!(params->voxel_x > 0) || !(params->voxel_y > 0) || !(params->voxel_z > 0) || !(params->cluster_tolerance > 0) ||
-        params->seg_max_iters < 0) { ctx->err = "invalid parameters"; return SP_ERR_ARG; }
+        params->seg_max_iters < 0) { ERR(ctx) = "invalid parameters"; return SP_ERR_ARG; }
     ctx->params = *params;
     make_consts(*params, ctx->d.c);
+    if (ctx->twin) { ctx->twin->params = *params; ctx->twin->d.c = ctx->d.c; }
     return SP_OK;
 }
 
-int sp_create(const sp_params *params, int device, int width, int height, int max_batch, sp_ctx **out)
+static int create_impl(const sp_params *params, int device, int width, int height, int max_batch, bool staging, sp_ctx **out)
 {
     if (!params || !out || width < 1 || height < 1 || max_batch < 1 || max_batch > 4096) { g_create_error = "bad argument"; return SP_ERR_ARG; }
     int ndev = 0;
@@ -349,6 +358,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     ctx->device = device; ctx->W = width; ctx->H = height; ctx->N = width * height; ctx->B = max_batch;
     { const char *t = getenv("SP_TRACE"); ctx->trace = t && *t && *t != '0'; }
     { const char *t = getenv("SP_KEY64"); ctx->force_key64 = t && *t && *t != '0'; }
+    { const char *t = getenv("SP_NO_TWIN"); ctx->no_twin = t && *t && *t != '0'; }
     memset(&ctx->d, 0, sizeof(ctx->d));
     memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
     auto fail = [&](const char *what, cudaError_t err) {
@@ -357,7 +367,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
         return SP_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
-    if (sp_set_params(ctx, params) != SP_OK) { g_create_error = ctx->err; sp_destroy(ctx); return SP_ERR_ARG; }
+    if (sp_set_params(ctx, params) != SP_OK) { g_create_error = ERR(ctx); sp_destroy(ctx); return SP_ERR_ARG; }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     for (int i = 0; i <= STG_COUNT; ++i) if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -370,7 +380,7 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     d.W = width; d.H = height; d.N = ctx->N; d.B = max_batch;
     d.nblk = (int)((N + 1023) / 1024);
 #define DA(ptr, n) if ((e = dalloc(ctx, &(ptr), (n))) != cudaSuccess) return fail("cudaMalloc " #ptr, e)
-    DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9);
+    if (staging) { DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9); }
     DA(d.xyzw, BN); DA(d.nrm, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
     DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 2);
@@ -415,9 +425,15 @@ int sp_create(const sp_params *params, int device, int width, int height, int ma
     return SP_OK;
 }
 
+int sp_create(const sp_params *params, int device, int width, int height, int max_batch, sp_ctx **out)
+{
+    return create_impl(params, device, width, height, max_batch, true, out);
+}
+
 void sp_destroy(sp_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->twin) { sp_destroy(ctx->twin); ctx->twin = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
@@ -460,16 +476,32 @@ void sp_rotation_from_quat(float w, float x, float y, float z, float *R9)
     mul(m3, m2, u); mul(u, m1, R9);
 }
 
+/* the twin lane of a context (created on first use; a batch that does not get one simply runs on a single lane) */
+static sp_ctx *twin_of(sp_ctx *ctx)
+{
+    if (ctx->no_twin || ctx->normal_mode != 0) return nullptr;
+    if (ctx->twin) return ctx->twin;
+    sp_ctx *t = nullptr;
+    if (create_impl(&ctx->params, ctx->device, ctx->W, ctx->H, ctx->B, false, &t) != SP_OK) { ctx->no_twin = true; (void)cudaGetLastError(); return nullptr; }
+    t->owner = ctx; t->trace = false; t->force_key64 = ctx->force_key64;
+    ctx->twin = t;
+    return t;
+}
+
 static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results, bool host_in)
 {
-    if (!ctx || !xyzrgba || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR || (!results && nframes > 0)) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    if (!ctx || !xyzrgba || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR || (!results && nframes > 0)) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     const size_t fb = (size_t)ctx->N * 16;
     if (show_mode == SP_SHOW_ORIGINAL) { memset(results, 0, sizeof(sp_frame_result) * (size_t)nframes); return SP_OK; }
     int buf = 0;
-    /* chunk loop; with host input the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i */
+    /* chunk loop; with host input the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i; with two or more
+     * chunks the chunks alternate between two lanes (this context and its twin), each with its own workspace and stream */
     const int nchunks = (nframes + ctx->B - 1) / ctx->B;
+    sp_ctx *lanes[2] = { ctx, ctx };
+    if (nchunks >= 2 && !ctx->trace) { sp_ctx *t = twin_of(ctx); if (t) lanes[1] = t; }
+    const bool two = lanes[1] != ctx;
     auto issue_copy = [&](int ci, int b) -> int {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
@@ -478,37 +510,48 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         CK(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
         return SP_OK;
     };
+    /* results travel behind the kernels: a chunk's records are copied out of their pinned buffer while later chunks run */
+    struct Pending { cudaEvent_t ev; const sp_frame_result *src; int f0, n; };
+    std::vector<Pending> pend;
+    size_t drained = 0;
+    auto drain = [&](size_t keep) -> int {
+        while (pend.size() - drained > keep) {
+            const Pending &q = pend[drained++];
+            CK(cudaEventSynchronize(q.ev));
+            memcpy(results + q.f0, q.src, sizeof(sp_frame_result) * (size_t)q.n);
+        }
+        return SP_OK;
+    };
     if (host_in && nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
+        sp_ctx *L = lanes[ci & 1];
+        const int hb = two ? (ci >> 1) & 1 : ci & 1;           /* the lane's pinned result buffer this chunk uses */
         const float4 *din; const float *dR;
         if (host_in) {
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
+            CK(cudaStreamWaitEvent(L->stream, ctx->ev_in[buf], 0));
             din = ctx->d_in[buf]; dR = R9 ? ctx->d_R[buf] : nullptr;
             if (ci + 1 < nchunks) { const int rc = issue_copy(ci + 1, buf ^ 1); if (rc) return rc; }
         } else {
             din = (const float4 *)((const uint8_t *)xyzrgba + fb * f0); dR = R9 ? R9 + 9 * (size_t)f0 : nullptr;
         }
-        CK(cudaMemsetAsync(ctx->d.results, 0, sizeof(sp_frame_result) * nB, ctx->stream));
-        const int rc = run_chunk(ctx, din, dR, nB, show_mode, -1);
+        CK(cudaMemsetAsync(L->d.results, 0, sizeof(sp_frame_result) * nB, L->stream));
+        const int rc = run_chunk(L, din, dR, nB, show_mode, -1);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
-        /* results travel one chunk behind: chunk ci is copied out of its pinned buffer while chunk ci + 1 runs */
-        CK(cudaMemcpyAsync(ctx->h_results + (size_t)(ci & 1) * ctx->B, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaEventRecord(ctx->ev_res[ci & 1], ctx->stream));
-        if (ci > 0) {
-            const int pf0 = (ci - 1) * ctx->B, pn = std::min(ctx->B, nframes - pf0);
-            CK(cudaEventSynchronize(ctx->ev_res[(ci - 1) & 1]));
-            memcpy(results + pf0, ctx->h_results + (size_t)((ci - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
-        }
+        CK(cudaEventRecord(ctx->ev_done[buf], L->stream));
+        CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
+        CK(cudaEventRecord(L->ev_res[hb], L->stream));
+        pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
+        { const int rd = drain(two ? 2 : 1); if (rd) return rd; }
         buf ^= 1;
     }
+    { const int rd = drain(0); if (rd) return rd; }
     if (nchunks > 0) {
-        const int pf0 = (nchunks - 1) * ctx->B, pn = nframes - pf0;
         CK(cudaStreamSynchronize(ctx->stream));
-        memcpy(results + pf0, ctx->h_results + (size_t)((nchunks - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
+        if (two) CK(cudaStreamSynchronize(lanes[1]->stream));
+        ctx->last = lanes[(nchunks - 1) & 1];
+        collect_times(ctx->last);
     }
-    collect_times(ctx);
     return SP_OK;
 }
 
@@ -516,8 +559,9 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
                             const float *R9, int nframes, int show_mode, sp_frame_result *results)
 {
     if (!ctx || !depth || !K || (depth_type != 0 && depth_type != 1) || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR ||
-        (!results && nframes > 0) || !(K->fx != 0.f) || !(K->fy != 0.f)) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+        (!results && nframes > 0) || !(K->fx != 0.f) || !(K->fy != 0.f)) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->last = nullptr;                                           /* this entry point runs on the context's own lane */
     CK(cudaSetDevice(ctx->device));
     if (show_mode == SP_SHOW_ORIGINAL) { memset(results, 0, sizeof(sp_frame_result) * (size_t)nframes); return SP_OK; }
     const size_t N = ctx->N, B = ctx->B, dsz = depth_type == 0 ? 4 : 2;
@@ -525,12 +569,12 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         cudaError_t e;
         for (int i = 0; i < 2; ++i) {
             void *q = nullptr;
-            if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ctx->err = std::string("cudaMalloc (depth staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+            if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (depth staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
             ctx->allocs.push_back(q); ctx->d_depth[i] = q;
-            if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ctx->err = std::string("cudaMalloc (colour staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+            if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (colour staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
             ctx->allocs.push_back(q); ctx->d_color[i] = (unsigned char *)q;
         }
-        if ((e = dalloc(ctx, &ctx->d_maps, (size_t)ctx->W + ctx->H)) != cudaSuccess) { ctx->err = std::string("cudaMalloc (maps): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+        if ((e = dalloc(ctx, &ctx->d_maps, (size_t)ctx->W + ctx->H)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (maps): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
     }
     {
         /* K2G::prepareMake3D, k2g.cpp:506-520: (i - c + 0.5) / f evaluated in double, stored as float */
@@ -550,35 +594,49 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         CK(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
         return SP_OK;
     };
+    /* two lanes like sp_process_frames: chunks alternate between this context and its twin */
+    sp_ctx *lanes[2] = { ctx, ctx };
+    if (nchunks >= 2 && !ctx->trace) { sp_ctx *t = twin_of(ctx); if (t) lanes[1] = t; }
+    const bool two = lanes[1] != ctx;
+    struct Pending { cudaEvent_t ev; const sp_frame_result *src; int f0, n; };
+    std::vector<Pending> pend;
+    size_t drained = 0;
+    auto drain = [&](size_t keep) -> int {
+        while (pend.size() - drained > keep) {
+            const Pending &q = pend[drained++];
+            CK(cudaEventSynchronize(q.ev));
+            memcpy(results + q.f0, q.src, sizeof(sp_frame_result) * (size_t)q.n);
+        }
+        return SP_OK;
+    };
     int buf = 0;
     if (nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
+        sp_ctx *L = lanes[ci & 1];
+        const int hb = two ? (ci >> 1) & 1 : ci & 1;
+        CK(cudaStreamWaitEvent(L->stream, ctx->ev_in[buf], 0));
         if (ci + 1 < nchunks) { const int rc = issue_copy(ci + 1, buf ^ 1); if (rc) return rc; }
-        k_depth_to_records<<<dim3(std::min(ctx->d.nblk, 148), nB), 256, 0, ctx->stream>>>(ctx->d_depth[buf], depth_type, bgrx ? ctx->d_color[buf] : nullptr,
-                                                                                             ctx->d_maps, ctx->d_maps + ctx->W, ctx->W, ctx->H, mirror ? 1 : 0, ctx->d_in[buf]);
-        ctx->launches += 1;
-        CK(cudaMemsetAsync(ctx->d.results, 0, sizeof(sp_frame_result) * nB, ctx->stream));
-        const int rc = run_chunk(ctx, ctx->d_in[buf], R9 ? ctx->d_R[buf] : nullptr, nB, show_mode, -1);
+        k_depth_to_records<<<dim3(std::min(ctx->d.nblk, 148), nB), 256, 0, L->stream>>>(ctx->d_depth[buf], depth_type, bgrx ? ctx->d_color[buf] : nullptr,
+                                                                                           ctx->d_maps, ctx->d_maps + ctx->W, ctx->W, ctx->H, mirror ? 1 : 0, ctx->d_in[buf]);
+        L->launches += 1;
+        CK(cudaMemsetAsync(L->d.results, 0, sizeof(sp_frame_result) * nB, L->stream));
+        const int rc = run_chunk(L, ctx->d_in[buf], R9 ? ctx->d_R[buf] : nullptr, nB, show_mode, -1);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
-        /* results travel one chunk behind: chunk ci is copied out of its pinned buffer while chunk ci + 1 runs */
-        CK(cudaMemcpyAsync(ctx->h_results + (size_t)(ci & 1) * ctx->B, ctx->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaEventRecord(ctx->ev_res[ci & 1], ctx->stream));
-        if (ci > 0) {
-            const int pf0 = (ci - 1) * ctx->B, pn = std::min(ctx->B, nframes - pf0);
-            CK(cudaEventSynchronize(ctx->ev_res[(ci - 1) & 1]));
-            memcpy(results + pf0, ctx->h_results + (size_t)((ci - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
-        }
+        CK(cudaEventRecord(ctx->ev_done[buf], L->stream));
+        CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
+        CK(cudaEventRecord(L->ev_res[hb], L->stream));
+        pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
+        { const int rd = drain(two ? 2 : 1); if (rd) return rd; }
         buf ^= 1;
     }
+    { const int rd = drain(0); if (rd) return rd; }
     if (nchunks > 0) {
-        const int pf0 = (nchunks - 1) * ctx->B, pn = nframes - pf0;
         CK(cudaStreamSynchronize(ctx->stream));
-        memcpy(results + pf0, ctx->h_results + (size_t)((nchunks - 1) & 1) * ctx->B, sizeof(sp_frame_result) * pn);
+        if (two) CK(cudaStreamSynchronize(lanes[1]->stream));
+        ctx->last = lanes[(nchunks - 1) & 1];
+        collect_times(ctx->last);
     }
-    collect_times(ctx);
     return SP_OK;
 }
 
@@ -594,9 +652,10 @@ int sp_process_frames_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_
 
 int sp_run_stage_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int stage)
 {
-    if (!ctx || !d_xyzrgba || nframes < 1 || nframes > ctx->B || stage < 0 || stage > 2) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    if (!ctx || !d_xyzrgba || nframes < 1 || nframes > ctx->B || stage < 0 || stage > 2) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
+    ctx->last = nullptr;
     return run_chunk(ctx, (const float4 *)d_xyzrgba, d_R9, nframes, SP_SHOW_STAIR, stage);
 }
 
@@ -605,6 +664,7 @@ void *sp_stream(sp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int sp_stage_ms(sp_ctx *ctx, float *out, int cap)
 {
     if (!ctx || !out) return 0;
+    ctx = lane_of_last_chunk(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     collect_times(ctx);
@@ -616,7 +676,7 @@ const char *sp_stage_name(int i) { return (i >= 0 && i < STG_COUNT) ? kStageName
 
 int sp_set_normal_mode(sp_ctx *ctx, int mode)
 {
-    if (!ctx || (mode != 0 && mode != 1)) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    if (!ctx || (mode != 0 && mode != 1)) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (mode == 1 && !ctx->knn_pts) {
@@ -625,7 +685,7 @@ int sp_set_normal_mode(sp_ctx *ctx, int mode)
         if ((e = dalloc(ctx, &ctx->knn_mm, B * 8)) != cudaSuccess || (e = dalloc(ctx, &ctx->knn_grid, B)) != cudaSuccess ||
             (e = dalloc(ctx, &ctx->knn_bstart, B << KNN_BITS)) != cudaSuccess || (e = dalloc(ctx, &ctx->knn_bend, B << KNN_BITS)) != cudaSuccess ||
             (e = dalloc(ctx, &ctx->knn_pts, B * N)) != cudaSuccess) {
-            ctx->err = std::string("cudaMalloc (kNN workspaces): ") + cudaGetErrorString(e);
+            ERR(ctx) = std::string("cudaMalloc (kNN workspaces): ") + cudaGetErrorString(e);
             ctx->knn_pts = nullptr;
             return SP_ERR_CUDA;
         }
@@ -648,12 +708,12 @@ int sp_trace_ms(sp_ctx *ctx, int i, const char **name, float *ms)
     if (cudaEventElapsedTime(ms, ctx->tev[i], ctx->tev[i + 1]) != cudaSuccess) { *ms = 0.f; (void)cudaGetLastError(); }
     return SP_OK;
 }
-int64_t sp_launch_count(const sp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t sp_launch_count(const sp_ctx *ctx) { return ctx ? ctx->launches + (ctx->twin ? ctx->twin->launches : 0) : 0; }
 
 /* ------------------------------------------------------------------------------------------------ taps */
 static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vector<uint8_t> &out)
 {
-    if (frame < 0 || frame >= ctx->last_nB) { ctx->err = "frame out of range"; return SP_ERR_ARG; }
+    if (frame < 0 || frame >= ctx->last_nB) { ERR(ctx) = "frame out of range"; return SP_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     const SpDev &d = ctx->d;
@@ -754,7 +814,7 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         std::vector<int> v(r.n_plane_points); CK(d2h(v.data(), d.plane_idx + f * N, (size_t)r.n_plane_points * 4));
         put_i(v); return SP_OK;
     }
-    ctx->err = "unknown tap: " + name;
+    ERR(ctx) = "unknown tap: " + name;
     return SP_ERR_ARG;
 }
 
@@ -763,7 +823,7 @@ int64_t sp_tap_bytes(sp_ctx *ctx, int frame, const char *name)
     if (!ctx || !name) return SP_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     std::vector<uint8_t> v;
-    const int rc = tap_build(ctx, frame, name, v);
+    const int rc = tap_build(lane_of_last_chunk(ctx), frame, name, v);
     return rc < 0 ? rc : (int64_t)v.size();
 }
 
@@ -772,7 +832,7 @@ int64_t sp_tap_copy(sp_ctx *ctx, int frame, const char *name, void *dst, int64_t
     if (!ctx || !name || (!dst && cap > 0)) return SP_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     std::vector<uint8_t> v;
-    const int rc = tap_build(ctx, frame, name, v);
+    const int rc = tap_build(lane_of_last_chunk(ctx), frame, name, v);
     if (rc < 0) return rc;
     const int64_t n = std::min<int64_t>(cap, (int64_t)v.size());
     if (n > 0) memcpy(dst, v.data(), (size_t)n);
@@ -781,14 +841,16 @@ int64_t sp_tap_copy(sp_ctx *ctx, int frame, const char *name, void *dst, int64_t
 
 int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t *pixel_idx, int cap)
 {
-    if (!ctx || frame < 0 || frame >= ctx->last_nB || plane < 0 || cap < 0) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    if (!ctx) return SP_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx = lane_of_last_chunk(ctx);
+    if (frame < 0 || frame >= ctx->last_nB || plane < 0 || cap < 0) { ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     const SpDev &d = ctx->d;
     const size_t N = ctx->N, f = frame;
     sp_frame_result r; CK(cudaMemcpy(&r, d.results + f, sizeof(r), cudaMemcpyDeviceToHost));
-    if (plane >= r.n_planes) { ctx->err = "plane out of range"; return SP_ERR_ARG; }
+    if (plane >= r.n_planes) { ERR(ctx) = "plane out of range"; return SP_ERR_ARG; }
     const int n = std::min(cap, r.planes[plane].count);
     std::vector<int> idx(n);
     if (n) CK(cudaMemcpy(idx.data(), d.plane_idx + f * N + r.planes[plane].first, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -843,8 +905,10 @@ struct DevicePoints : sp_stairmodel::StairPoints {
 
 int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out)
 {
-    if (!ctx || !out || frame < 0 || frame >= ctx->last_nB) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    if (!ctx) return SP_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx = lane_of_last_chunk(ctx);
+    if (!out || frame < 0 || frame >= ctx->last_nB) { ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<sp_frame_result> fr(1);
@@ -885,15 +949,17 @@ int sp_pack_robot(const sp_result_def *result, uint8_t *out19)
 int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, const float *dir3, float *max_xyz, float *min_xyz,
                    int32_t *max_pixel, int32_t *min_pixel)
 {
-    if (!ctx || !dir3 || frame < 0 || frame >= ctx->last_nB || plane < 0) { if (ctx) ctx->err = "bad argument"; return SP_ERR_ARG; }
+    if (!ctx) return SP_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx = lane_of_last_chunk(ctx);
+    if (!dir3 || frame < 0 || frame >= ctx->last_nB || plane < 0) { ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     const SpDev &d = ctx->d;
     const size_t N = ctx->N, f = frame;
     sp_frame_result *r = new sp_frame_result;
     cudaError_t e = cudaMemcpy(r, d.results + f, sizeof(*r), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess || plane >= r->n_planes) { const bool bad = e == cudaSuccess; delete r; ctx->err = bad ? "plane out of range" : cudaGetErrorString(e); return bad ? SP_ERR_ARG : SP_ERR_CUDA; }
+    if (e != cudaSuccess || plane >= r->n_planes) { const bool bad = e == cudaSuccess; delete r; ERR(ctx) = bad ? "plane out of range" : cudaGetErrorString(e); return bad ? SP_ERR_ARG : SP_ERR_CUDA; }
     const sp_plane_record pr = r->planes[plane];
     delete r;
     const float *c = center3 ? center3 : pr.center;

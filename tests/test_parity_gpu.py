@@ -401,3 +401,42 @@ def test_normals_without_the_exactness_guarantee(sp, orc, synth):
         bad = compare_frame(ctx, i, res[i], o)
         assert not bad, "frame %d\n" % i + "\n".join(bad[:20])
     ctx.close()
+
+
+def test_two_lane_chunk_pipeline_keeps_order_and_bits(sp, synth, monkeypatch):
+    """batches of two or more chunks alternate between a context and its twin lane (own workspace, own stream): eleven frames
+    through chunks of two must give, record by record, what one big chunk gives -- from host clouds, from device-resident clouds,
+    from depth images, and with the twin switched off (SP_NO_TWIN=1)"""
+    import torch
+    frames = [synth.make_frame(f) for f in (21, 22, 23)]
+    recs = np.stack([frames[i % 3][0] for i in range(11)])
+    Rs = np.stack([frames[i % 3][1] for i in range(11)])
+    big = sp.Context(device=0, width=512, height=424, max_batch=11)
+    want = big.process_frames(recs, Rs).copy()
+    big.close()
+    assert int(want["n_planes"].min()) >= 8
+    for no_twin in (False, True):
+        if no_twin:
+            monkeypatch.setenv("SP_NO_TWIN", "1")
+        ctx = sp.Context(device=0, width=512, height=424, max_batch=2)
+        got = ctx.process_frames(recs, Rs)
+        assert got.tobytes() == want.tobytes()
+        d_c = torch.from_numpy(recs.view(np.uint8).reshape(11, -1)).cuda()
+        d_R = torch.from_numpy(Rs).cuda()
+        torch.cuda.synchronize()
+        got = ctx.process_frames(d_c, d_R, device_input=True, nframes=11)
+        assert got.tobytes() == want.tobytes()
+        # the last chunk (frame 10 alone) ran on lane 0 or 1: its taps must be that frame's
+        assert ctx.tap(0, "plane_idx").size == int(want[10]["n_plane_points"])
+        ctx.close()
+    monkeypatch.delenv("SP_NO_TWIN")
+    dfr = [synth.make_depth_frame(f) for f in (21, 22, 23)]
+    depth = np.stack([dfr[i % 3][0] for i in range(7)])
+    bgrx = np.stack([dfr[i % 3][1] for i in range(7)])
+    one = sp.Context(device=0, width=512, height=424, max_batch=7)
+    want_d = one.process_depth_frames(depth, synth.INTRINSICS, bgrx=bgrx, mirror=True, R=Rs[:7], nframes=7).copy()
+    one.close()
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=2)
+    got_d = ctx.process_depth_frames(depth, synth.INTRINSICS, bgrx=bgrx, mirror=True, R=Rs[:7], nframes=7)
+    assert got_d.tobytes() == want_d.tobytes()
+    ctx.close()
