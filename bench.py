@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A step = one pass of the whole front-end (levelling .. sorted plane records) over this rank's batch of frames.
-`value`  : device-resident input (HBM), includes the D2H of the per-frame plane records and, for N > 1, the gather.
+`value`  : device-resident input (HBM), includes the D2H of the per-frame plane records and, for N > 1, the gather.  The
+           library runs the chunks of a batch on two lanes (context + twin workspace), see DESIGN.md section 2.
 `e2e`    : the same metric through sp_process_frames with pinned HOST buffers (H2D + D2H inside the timed region).
 `roofline`: the fused ingest+normals kernel (K1K2) timed with CUDA events on the library's stream.
 `cpu_baseline` / `--impl reference`: the CPU oracle (a port: the reference's PCL build cannot be compiled in this
@@ -392,6 +393,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config 5: batch of synthetic Kinect-V2 4-step stair frames, 512x424 (217088 pts), levelling + full segmentation front-end",
                        "frames_per_gpu_per_step": F, "distinct_frames": N_DISTINCT, "max_batch": args.max_batch,
+                       "lanes": 1 if os.environ.get("SP_NO_TWIN", "") not in ("", "0") else 2,
                        "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (F * N * 16 / 1e9), "parallelism": "frames sharded across %d GPU(s)" % world,
                        "host_numa_binding": numa_node},
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 16 + 36)),
