@@ -122,7 +122,7 @@ void sp_rotation_from_quat(float w, float x, float y, float z, float *R9);
  * the call loops over chunks, and from the second chunk on alternates between two lanes: the context's own workspace and
  * a twin (same size, created on first use on the same device, own stream), so that one chunk's latency-bound tail overlaps
  * the next chunk's streaming head.  The environment variable SP_NO_TWIN=1 (read at sp_create) keeps a single lane and a
- * single workspace.  Results, taps and the stair model do not depend on the lane count.  show_mode: SP_SHOW_*
+ * single workspace; SP_LANES=n (1..4, default 2) sets the lane count (three lanes measured the same as two, four slower).  Results, taps and the stair model do not depend on the lane count.  show_mode: SP_SHOW_*
  * (SP_SHOW_ORIGINAL does no work, StairPerception.cpp:24; the other taps stop the pipeline where process() returns early). */
 int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode,
                       sp_frame_result *results);

@@ -135,7 +135,8 @@ struct sp_ctx {
     /* second lane: batches of two or more chunks alternate between this context and a twin (own workspace, own stream), so that
      * the issue- and latency-bound tail of one chunk (clustering, RANSAC, plane statistics) shares the SMs with the streaming
      * head of the next.  The twin is created on first use and shares the input staging buffers of its owner. */
-    sp_ctx *twin = nullptr, *owner = nullptr;
+    sp_ctx *twin = nullptr, *owner = nullptr; /* twins chain: ctx -> twin -> twin's twin (SP_LANES, default 2, at most 4) */
+    int want_lanes = 2;
     sp_ctx *last = nullptr;                   /* the lane that ran the last chunk: taps, stair model, stage times read it */
     bool no_twin = false;                     /* SP_NO_TWIN=1 */
 };
@@ -341,7 +342,7 @@ int sp_set_params(sp_ctx *ctx, const sp_params *params)
         params->seg_max_iters < 0) { ERR(ctx) = "invalid parameters"; return SP_ERR_ARG; }
     ctx->params = *params;
     make_consts(*params, ctx->d.c);
-    if (ctx->twin) { ctx->twin->params = *params; ctx->twin->d.c = ctx->d.c; }
+    for (sp_ctx *t = ctx->twin; t; t = t->twin) { t->params = *params; t->d.c = ctx->d.c; }
     return SP_OK;
 }
 
@@ -359,6 +360,7 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     { const char *t = getenv("SP_TRACE"); ctx->trace = t && *t && *t != '0'; }
     { const char *t = getenv("SP_KEY64"); ctx->force_key64 = t && *t && *t != '0'; }
     { const char *t = getenv("SP_NO_TWIN"); ctx->no_twin = t && *t && *t != '0'; }
+    { const char *t = getenv("SP_LANES"); if (t && *t) ctx->want_lanes = std::max(1, std::min(4, atoi(t))); if (ctx->want_lanes < 2) ctx->no_twin = true; }
     memset(&ctx->d, 0, sizeof(ctx->d));
     memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
     auto fail = [&](const char *what, cudaError_t err) {
@@ -477,15 +479,29 @@ void sp_rotation_from_quat(float w, float x, float y, float z, float *R9)
 }
 
 /* the twin lane of a context (created on first use; a batch that does not get one simply runs on a single lane) */
-static sp_ctx *twin_of(sp_ctx *ctx)
+static sp_ctx *twin_of(sp_ctx *ctx, sp_ctx *after)
 {
     if (ctx->no_twin || ctx->normal_mode != 0) return nullptr;
-    if (ctx->twin) return ctx->twin;
+    if (after->twin) return after->twin;
     sp_ctx *t = nullptr;
     if (create_impl(&ctx->params, ctx->device, ctx->W, ctx->H, ctx->B, false, &t) != SP_OK) { ctx->no_twin = true; (void)cudaGetLastError(); return nullptr; }
     t->owner = ctx; t->trace = false; t->force_key64 = ctx->force_key64;
-    ctx->twin = t;
+    after->twin = t;
     return t;
+}
+
+/* the lanes a batch of nchunks chunks runs on: the context itself, then as many twins as wanted and as the batch can use */
+static int lanes_for(sp_ctx *ctx, int nchunks, sp_ctx **lanes)
+{
+    int nl = 1;
+    lanes[0] = ctx;
+    if (ctx->trace) return nl;
+    while (nl < ctx->want_lanes && nl < nchunks) {
+        sp_ctx *t = twin_of(ctx, lanes[nl - 1]);
+        if (!t) break;
+        lanes[nl++] = t;
+    }
+    return nl;
 }
 
 static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results, bool host_in)
@@ -499,9 +515,8 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
     /* chunk loop; with host input the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i; with two or more
      * chunks the chunks alternate between two lanes (this context and its twin), each with its own workspace and stream */
     const int nchunks = (nframes + ctx->B - 1) / ctx->B;
-    sp_ctx *lanes[2] = { ctx, ctx };
-    if (nchunks >= 2 && !ctx->trace) { sp_ctx *t = twin_of(ctx); if (t) lanes[1] = t; }
-    const bool two = lanes[1] != ctx;
+    sp_ctx *lanes[4];
+    const int nl = lanes_for(ctx, nchunks, lanes);
     auto issue_copy = [&](int ci, int b) -> int {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
@@ -525,8 +540,8 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
     if (host_in && nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
-        sp_ctx *L = lanes[ci & 1];
-        const int hb = two ? (ci >> 1) & 1 : ci & 1;           /* the lane's pinned result buffer this chunk uses */
+        sp_ctx *L = lanes[ci % nl];
+        const int hb = (ci / nl) & 1;                          /* the lane's pinned result buffer this chunk uses */
         const float4 *din; const float *dR;
         if (host_in) {
             CK(cudaStreamWaitEvent(L->stream, ctx->ev_in[buf], 0));
@@ -542,14 +557,13 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
         CK(cudaEventRecord(L->ev_res[hb], L->stream));
         pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
-        { const int rd = drain(two ? 2 : 1); if (rd) return rd; }
+        { const int rd = drain((size_t)nl); if (rd) return rd; }
         buf ^= 1;
     }
     { const int rd = drain(0); if (rd) return rd; }
     if (nchunks > 0) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (two) CK(cudaStreamSynchronize(lanes[1]->stream));
-        ctx->last = lanes[(nchunks - 1) & 1];
+        for (int l = 0; l < nl; ++l) CK(cudaStreamSynchronize(lanes[l]->stream));
+        ctx->last = lanes[(nchunks - 1) % nl];
         collect_times(ctx->last);
     }
     return SP_OK;
@@ -595,9 +609,8 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         return SP_OK;
     };
     /* two lanes like sp_process_frames: chunks alternate between this context and its twin */
-    sp_ctx *lanes[2] = { ctx, ctx };
-    if (nchunks >= 2 && !ctx->trace) { sp_ctx *t = twin_of(ctx); if (t) lanes[1] = t; }
-    const bool two = lanes[1] != ctx;
+    sp_ctx *lanes[4];
+    const int nl = lanes_for(ctx, nchunks, lanes);
     struct Pending { cudaEvent_t ev; const sp_frame_result *src; int f0, n; };
     std::vector<Pending> pend;
     size_t drained = 0;
@@ -613,8 +626,8 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
     if (nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
-        sp_ctx *L = lanes[ci & 1];
-        const int hb = two ? (ci >> 1) & 1 : ci & 1;
+        sp_ctx *L = lanes[ci % nl];
+        const int hb = (ci / nl) & 1;
         CK(cudaStreamWaitEvent(L->stream, ctx->ev_in[buf], 0));
         if (ci + 1 < nchunks) { const int rc = issue_copy(ci + 1, buf ^ 1); if (rc) return rc; }
         k_depth_to_records<<<dim3(std::min(ctx->d.nblk, 148), nB), 256, 0, L->stream>>>(ctx->d_depth[buf], depth_type, bgrx ? ctx->d_color[buf] : nullptr,
@@ -627,14 +640,13 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
         CK(cudaEventRecord(L->ev_res[hb], L->stream));
         pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
-        { const int rd = drain(two ? 2 : 1); if (rd) return rd; }
+        { const int rd = drain((size_t)nl); if (rd) return rd; }
         buf ^= 1;
     }
     { const int rd = drain(0); if (rd) return rd; }
     if (nchunks > 0) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (two) CK(cudaStreamSynchronize(lanes[1]->stream));
-        ctx->last = lanes[(nchunks - 1) & 1];
+        for (int l = 0; l < nl; ++l) CK(cudaStreamSynchronize(lanes[l]->stream));
+        ctx->last = lanes[(nchunks - 1) % nl];
         collect_times(ctx->last);
     }
     return SP_OK;
@@ -708,7 +720,7 @@ int sp_trace_ms(sp_ctx *ctx, int i, const char **name, float *ms)
     if (cudaEventElapsedTime(ms, ctx->tev[i], ctx->tev[i + 1]) != cudaSuccess) { *ms = 0.f; (void)cudaGetLastError(); }
     return SP_OK;
 }
-int64_t sp_launch_count(const sp_ctx *ctx) { return ctx ? ctx->launches + (ctx->twin ? ctx->twin->launches : 0) : 0; }
+int64_t sp_launch_count(const sp_ctx *ctx) { int64_t n = 0; for (const sp_ctx *t = ctx; t; t = t->twin) n += t->launches; return n; }
 
 /* ------------------------------------------------------------------------------------------------ taps */
 static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vector<uint8_t> &out)
