@@ -31,13 +31,14 @@
 #define K1_GH (K1_TH + 4)
 #define K1_THREADS 256
 
-#define K1_BAND 8                         /* tile rows per column-sum band of the exact path */
+#define K1_BAND0 8                        /* tile rows of the first column-sum band of the exact path (computed while S3 runs) ... */
+#define K1_BAND 12                        /* ... and of the following ones */
 struct K1Smem {                           /* 54.9 KB: four CTAs per SM */
-    float sz[K1_RH * K1_RW];              /* sz, sx, sy are contiguous: the exact path re-uses them as its column-sum band */
+    float sz[K1_RH * K1_RW];              /* sz .. fbhi are contiguous: the exact path re-uses them as its column-sum band */
     float sx[K1_XH * K1_XW], sy[K1_XH * K1_XW];
-    float gx[3][K1_GH * K1_GW], gy[3][K1_GH * K1_GW];
     unsigned long long dil[5][K1_FH];     /* bit rows of the flag region (bit c = column c): depth-change pixels dilated by 0..4 columns */
-    unsigned falo[K1_GH], fahi[K1_GH], fblo[K1_GH], fbhi[K1_GH];   /* finite dx / dy gradient elements per gradient row, same split */
+    unsigned falo[K1_GH], fahi[K1_GH], fblo[K1_GH], fbhi[K1_GH];   /* finite dx / dy gradient elements per gradient row: columns 0..31, 32..35 */
+    float gx[3][K1_GH * K1_GW], gy[3][K1_GH * K1_GW];
     unsigned kmask[4][K1_TH];             /* per tile row: pixels whose smoothing window is 5, 4, 3, 2 */
     unsigned vmask[K1_TH], imask[K1_TH];  /* pixels that may get a normal (image border, finite z); pixels inside the image */
     unsigned short base[3][K1_TH];        /* where a row's window-5 / window-4 / window-3-and-2 pixels start in their list */
@@ -46,8 +47,9 @@ struct K1Smem {                           /* 54.9 KB: four CTAs per SM */
     int n5, n4, n32, pad;
 };
 static_assert(K1_FW <= 64 && K1_TW == 32 && K1_FH % 4 == 0, "bit rows: one 64-bit word per flag row, one warp lane per tile column");
-static_assert(6 * K1_BAND * K1_GW * sizeof(double) <= (K1_RH * K1_RW + 2 * K1_XH * K1_XW) * sizeof(float), "column-sum band must fit in sz + sx + sy");
-static_assert(K1_TH % K1_BAND == 0 && 6 * K1_GW <= K1_THREADS, "one thread per (channel, gradient column)");
+static_assert(6 * K1_BAND0 * K1_GW * sizeof(double) <= (K1_RH * K1_RW + 2 * K1_XH * K1_XW) * sizeof(float), "the first band must stay inside sz + sx + sy (S3 still reads dil)");
+static_assert(6 * K1_BAND * K1_GW * sizeof(double) <= offsetof(K1Smem, gx), "column-sum band must fit in front of the gradients");
+static_assert(offsetof(K1Smem, dil) % 8 == 0 && (K1_TH - K1_BAND0) % K1_BAND == 0 && 6 * K1_GW <= K1_THREADS - 32, "layout / one thread per (channel, gradient column)");
 
 __device__ __forceinline__ bool k1_bad_pair(float za, float zb)
 {
@@ -103,21 +105,22 @@ __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e
     k1_finish(d, gi, pw.x, pw.y, pw.z, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
 }
 
-/* Exact path, first half: thread u < 6 * K1_GW = (channel, gradient column) slides a 5-row column sum down the K1_BAND tile rows
+/* Exact path, first half: thread u < 6 * K1_GW = (channel, gradient column) slides a 5-row column sum down the ROWS tile rows
  * from b0 on and leaves them in csum[channel][row][column] */
+template <int ROWS>
 __device__ __forceinline__ void k1_column_sums(const K1Smem &s, double *csum, int u, int b0)
 {
     const int ch = u / K1_GW, col = u - ch * K1_GW;
     if (ch >= 6) return;
     const float *g = ch < 3 ? s.gx[ch] : s.gy[ch - 3];
-    float v[K1_BAND + 4];
+    float v[ROWS + 4];
 #pragma unroll
-    for (int a = 0; a < K1_BAND + 4; ++a) v[a] = g[(b0 + a) * K1_GW + col];
+    for (int a = 0; a < ROWS + 4; ++a) v[a] = g[(b0 + a) * K1_GW + col];
     double w = (double)v[0] + (double)v[1] + (double)v[2] + (double)v[3];
 #pragma unroll
-    for (int i = 0; i < K1_BAND; ++i) {
+    for (int i = 0; i < ROWS; ++i) {
         w += (double)v[i + 4];
-        csum[(ch * K1_BAND + i) * K1_GW + col] = w;
+        csum[(ch * ROWS + i) * K1_GW + col] = w;
         w -= (double)v[i];
     }
 }
@@ -143,7 +146,10 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
     const float qnan = __int_as_float(0x7fc00000);
     const size_t tile_base = (size_t)f * N + (size_t)r0 * W + c0;
 
-    /* S0: load tile + halo, level, mask -> shared memory (flat index, row / column kept incrementally: 256 = 6 * 42 + 4) */
+    /* S0: load tile + halo, level, mask -> shared memory.  The owned 32 x 32 block goes first, one warp per tile row (lane =
+     * column, coalesced 512-byte rows): besides the shared-memory copy each pixel is stored levelled (packed float4) and enters
+     * the crop statistics of passThroughCloudANDNormal / getMinMax3D, the cropped pixels per 1024-pixel block for the voxel stage
+     * and the row masks; the 740 halo elements follow in a flat loop. */
     bool risk = false;
     {
         float R[9];
@@ -152,49 +158,37 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
 #pragma unroll
             for (int i = 0; i < 9; ++i) R[i] = __ldg(d.R + 9 * f + i);
         }
-        int rr = tid / K1_RW, cc = tid - rr * K1_RW;
-        for (int e = tid; e < K1_RH * K1_RW; e += K1_THREADS) {
-            const int gr = r0 - K1_HALO + rr, gc = c0 - K1_HALO + cc;
-            float ox = qnan, oy = qnan, oz = qnan;
-            if (gr >= 0 && gr < H && gc >= 0 && gc < W) {
-                const float4 p = __ldg(in + (size_t)gr * W + gc);
-                ox = p.x; oy = p.y; oz = p.z;
-                if (rot) {
-                    if (!isnan(p.x)) {
-                        ox = R[0] * p.x + R[1] * p.y + R[2] * p.z;
-                        oy = R[3] * p.x + R[4] * p.y + R[5] * p.z;
-                        oz = R[6] * p.x + R[7] * p.y + R[8] * p.z;
-                    } else { ox = oy = oz = qnan; }
-                }
-                /* remove_nan_points: r, g or b == 0 marks an invalid pixel (per-byte compare of the three colour bytes) */
-                if (__vcmpeq4(__float_as_uint(p.w) | 0xff000000u, 0u)) { ox = oy = oz = qnan; }
+        auto level = [&](const float4 &p, float &ox, float &oy, float &oz) {
+            ox = p.x; oy = p.y; oz = p.z;
+            if (rot) {
+                if (!isnan(p.x)) {
+                    ox = R[0] * p.x + R[1] * p.y + R[2] * p.z;
+                    oy = R[3] * p.x + R[4] * p.y + R[5] * p.z;
+                    oz = R[6] * p.x + R[7] * p.y + R[8] * p.z;
+                } else { ox = oy = oz = qnan; }
             }
-            s.sz[e] = oz;
-            risk |= k1_inexact_risk(ox) | k1_inexact_risk(oy) | k1_inexact_risk(oz);
-            const unsigned xr = (unsigned)(rr - 2), xc = (unsigned)(cc - 2);       /* x, y keep a halo of 3 */
-            if (xr < (unsigned)K1_XH && xc < (unsigned)K1_XW) { s.sx[xr * K1_XW + xc] = ox; s.sy[xr * K1_XW + xc] = oy; }
-            cc += K1_THREADS % K1_RW; rr += K1_THREADS / K1_RW;
-            if (cc >= K1_RW) { cc -= K1_RW; ++rr; }
-        }
-    }
-    const bool exact = __syncthreads_or(risk) == 0;      /* box sums of this tile are exact in double in any order */
-
-    /* S0b: the owned pixels, one warp per tile row (lane = column): levelled xyz out, crop statistics of
-     * passThroughCloudANDNormal / getMinMax3D, cropped pixels per 1024-pixel block for the voxel stage, row masks */
-    {
+            /* remove_nan_points: r, g or b == 0 marks an invalid pixel (per-byte compare of the three colour bytes) */
+            if (__vcmpeq4(__float_as_uint(p.w) | 0xff000000u, 0u)) { ox = oy = oz = qnan; }
+        };
         float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
         int nvalid = 0, ncrop = 0;
         const int gc = c0 + lane;
+        float4 pv[K1_TH / 8];                                             /* the thread's four records are requested together */
+#pragma unroll
+        for (int it = 0; it < K1_TH / 8; ++it) {
+            const int gr = r0 + it * 8 + wid;
+            pv[it] = make_float4(qnan, qnan, qnan, __int_as_float(-1));
+            if (gr < H && gc < W) pv[it] = __ldg(in + (size_t)gr * W + gc);
+        }
 #pragma unroll
         for (int it = 0; it < K1_TH / 8; ++it) {
             const int tr = it * 8 + wid, gr = r0 + tr;
-            const int xe = (tr + 3) * K1_XW + lane + 3;
-            const float ox = s.sx[xe], oy = s.sy[xe], oz = s.sz[(tr + K1_HALO) * K1_RW + lane + K1_HALO];
             const bool inside = gr < H && gc < W;
+            float ox = qnan, oy = qnan, oz = qnan;
             bool crop = false;
             if (inside) {
-                const size_t gi = tile_base + (size_t)tr * W + lane;
-                d.xyzw[gi] = make_float4(ox, oy, oz, 0.f);
+                level(pv[it], ox, oy, oz);
+                d.xyzw[tile_base + (size_t)tr * W + lane] = make_float4(ox, oy, oz, 0.f);
                 if (sp_finite3(ox, oy, oz)) {
                     ++nvalid;
                     if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {
@@ -204,6 +198,9 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
                     }
                 }
             }
+            s.sz[(tr + K1_HALO) * K1_RW + lane + K1_HALO] = oz;
+            s.sx[(tr + 3) * K1_XW + lane + 3] = ox; s.sy[(tr + 3) * K1_XW + lane + 3] = oy;
+            risk |= k1_inexact_risk(ox) | k1_inexact_risk(oy) | k1_inexact_risk(oz);
             const unsigned bc = __ballot_sync(0xffffffffu, crop);
             const unsigned bi = __ballot_sync(0xffffffffu, inside);
             const unsigned bv = __ballot_sync(0xffffffffu, inside && gr >= 5 && gr < H - 5 && gc >= 5 && gc < W - 5 && sp_finite(oz));
@@ -230,7 +227,22 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
             }
         }
         if (lane == 0 && nvalid) atomicAdd(&d.counts[f * SP_NCOUNT + 1], nvalid);
+        /* the halo ring: 5 rows of 42 above, 5 below, 32 rows of 5 + 5 at the sides */
+        constexpr int RING_TB = K1_HALO * K1_RW, RING = 2 * RING_TB + K1_TH * 2 * K1_HALO;
+        for (int e = tid; e < RING; e += K1_THREADS) {
+            int rr, cc;
+            if (e < 2 * RING_TB) { const int q = e < RING_TB ? e : e - RING_TB; rr = q / K1_RW; cc = q - rr * K1_RW; if (e >= RING_TB) rr += K1_HALO + K1_TH; }
+            else { const int q = e - 2 * RING_TB; rr = q / (2 * K1_HALO); cc = q - rr * (2 * K1_HALO); rr += K1_HALO; if (cc >= K1_HALO) cc += K1_TW; }
+            const int gr = r0 - K1_HALO + rr, gc2 = c0 - K1_HALO + cc;
+            float ox = qnan, oy = qnan, oz = qnan;
+            if (gr >= 0 && gr < H && gc2 >= 0 && gc2 < W) level(__ldg(in + (size_t)gr * W + gc2), ox, oy, oz);
+            s.sz[rr * K1_RW + cc] = oz;
+            risk |= k1_inexact_risk(ox) | k1_inexact_risk(oy) | k1_inexact_risk(oz);
+            const unsigned xr = (unsigned)(rr - 2), xc = (unsigned)(cc - 2);       /* x, y keep a halo of 3 */
+            if (xr < (unsigned)K1_XH && xc < (unsigned)K1_XW) { s.sx[xr * K1_XW + xc] = ox; s.sy[xr * K1_XW + xc] = oy; }
+        }
     }
+    const bool exact = __syncthreads_or(risk) == 0;      /* box sums of this tile are exact in double in any order */
 
     /* S1 + S2: depth-change flags on the lateral coordinate z (reference quirk), halo 4, as bit rows, four flag rows per warp
      * pass: columns 0..31 of each row (the ballot is the row), then the eight tail columns of the four rows in one go; lanes
@@ -281,8 +293,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
      * "window <= k" is therefore an OR of dilated rows; the list offsets of each row come from a warp scan of the counts.
      * Meanwhile warps 1..7 of an exact tile start on the separable sums of S5 (column sums of the first band): the coordinates
      * in sz / sx / sy had their last readers before the barrier above, the band may overwrite them. */
-    double *csum = reinterpret_cast<double *>(k1_raw);                      /* [6][K1_BAND][K1_GW], over sz / sx / sy */
-    if (exact && tid >= 32) k1_column_sums(s, csum, tid - 32, 0);
+    double *csum = reinterpret_cast<double *>(k1_raw);                      /* [6][band rows][K1_GW], over sz / sx / sy (+ dil, fa / fb rows) */
+    if (exact && tid >= 32) k1_column_sums<K1_BAND0>(s, csum, tid - 32, 0);
     if (tid < K1_TH) {
         const int r = tid + 4;
         const unsigned long long (*D)[K1_FH] = s.dil;
@@ -342,11 +354,12 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
      * (and of 5 in a tile without the exactness guarantee) take the ordered sums; they are handed out from the last thread
      * downwards, to the threads the first band leaves idle. */
     const int n5 = s.n5, n4 = s.n4, n32 = min(s.n32, K1_TH * K1_TW / 2);
-    for (int b0 = 0; b0 < (exact ? (n5 ? K1_TH : K1_BAND) : 0); b0 += K1_BAND) {    /* CTA-uniform bounds */
-        const int p0 = s.base[0][b0], p1 = b0 + K1_BAND < K1_TH ? s.base[0][b0 + K1_BAND] : n5;
+    for (int b0 = 0; b0 < (exact ? (n5 ? K1_TH : K1_BAND0) : 0); b0 += (b0 ? K1_BAND : K1_BAND0)) {    /* CTA-uniform bounds */
+        const int rows = b0 ? K1_BAND : K1_BAND0;                           /* bands of 8, 12, 12 tile rows */
+        const int p0 = s.base[0][b0], p1 = b0 + rows < K1_TH ? s.base[0][b0 + rows] : n5;
         if (b0 > 0) {                                                       /* the first band's column sums are there already */
             __syncthreads();
-            if (p1 > p0) k1_column_sums(s, csum, tid, b0);
+            if (p1 > p0) k1_column_sums<K1_BAND>(s, csum, tid, b0);
             __syncthreads();
         }
         for (int i = p0 + tid; i < p1; i += K1_THREADS) {
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
             double sg[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                const double *q = c + k * K1_BAND * K1_GW;
+                const double *q = c + k * rows * K1_GW;
                 sg[k] = q[0] + q[1] + q[2] + q[3] + q[4];
             }
             const size_t gi = tile_base + (size_t)rr * W + cc;
