@@ -415,8 +415,11 @@ def test_two_lane_chunk_pipeline_keeps_order_and_bits(sp, synth, monkeypatch):
     want = big.process_frames(recs, Rs).copy()
     big.close()
     assert int(want["n_planes"].min()) >= 8
-    for no_twin in (False, True):
-        if no_twin:
+    for no_twin in (False, "3 lanes", True):
+        if no_twin == "3 lanes":
+            monkeypatch.setenv("SP_LANES", "3")
+        elif no_twin:
+            monkeypatch.delenv("SP_LANES")
             monkeypatch.setenv("SP_NO_TWIN", "1")
         ctx = sp.Context(device=0, width=512, height=424, max_batch=2)
         got = ctx.process_frames(recs, Rs)
