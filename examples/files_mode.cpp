@@ -62,6 +62,18 @@ int main(int argc, char **argv)
             for (int i = 0; i < stair_model.n_nodes; ++i)
                 if (stair_model.nodes[i].kind == 1)
                     std::printf("%g\t%g\t%g\t%g\n", stair_model.nodes[i].height, stair_model.nodes[i].depth, (double)stair_model.nodes[i].line_h, (double)stair_model.nodes[i].line_d);
+            if (has_stair) {
+                // what the GUI draws per plane (computePlaneCounter, StairPerception.cpp:2861-3075; gui.cpp:326-330): the closed contours
+                std::printf("side planes: left %g %g %g %g  right %g %g %g %g\n", (double)stair_model.slide_left[0], (double)stair_model.slide_left[1],
+                            (double)stair_model.slide_left[2], (double)stair_model.slide_left[3], (double)stair_model.slide_right[0], (double)stair_model.slide_right[1],
+                            (double)stair_model.slide_right[2], (double)stair_model.slide_right[3]);
+                for (size_t k = 0; k < vector_plane_sorted.size() && k < (size_t)SP_MAX_PLANES; ++k) {
+                    if (stair_model.contour_width[k] != 4) continue;
+                    std::printf("contour plane %zu:", k);
+                    for (int c = 0; c < 4; ++c) std::printf(" (%.3f %.3f %.3f)", (double)stair_model.contour[k][c][0], (double)stair_model.contour[k][c][1], (double)stair_model.contour[k][c][2]);
+                    std::printf("\n");
+                }
+            }
         }
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
