@@ -173,6 +173,8 @@ def test_cpp_facade_matches_oracle(sp, orc, samples):
             assert int(t[0]) == int(p["type"]) and int(t[1]) == int(p["count"])
             got = np.array([float.fromhex(v) for v in t[2:9]], dtype=np.float32)
             assert same_bits(got, np.concatenate([p["coef"], p["center"]]))
+        if name == "0001":                                   # four steps: the contours of their treads and risers are closed
+            assert any(l.startswith("side planes:") for l in lines) and sum(l.startswith("contour plane") for l in lines) >= 7
     # a tap through the facade: horizontal cloud
     r = subprocess.run([os.path.join(ROOT, "examples", "files_mode"), os.path.join(ROOT, "tests", "golden", "samples", "0000_cloud.pcd"), "4"],
                        capture_output=True, text=True, check=True)
