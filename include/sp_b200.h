@@ -118,7 +118,11 @@ void sp_rotation_from_quat(float w, float x, float y, float z, float *R9);
  *   R9      : nframes x 9 row-major levelling rotations, or NULL = already levelled (files mode, reader.cpp:493)
  *   results : nframes records, caller-allocated
  * sp_process_frames takes HOST pointers (copies inside); sp_process_frames_device takes DEVICE pointers to
- * inputs already resident in HBM and still writes `results` to host memory.  nframes may exceed max_batch:
+ * inputs already resident in HBM and still writes `results` to host memory.
+ * ORDERING PRECONDITION of the *_device entry points (also sp_run_stage_device): the library launches on its own
+ * non-blocking streams and does not know the stream that produced d_xyzrgba / d_R9.  The caller must make those
+ * buffers complete before the call (cudaStreamSynchronize / cudaEventSynchronize on the producer) and must not
+ * overwrite them until the call returns.  The Python binding synchronises torch's current stream for CUDA tensors.  nframes may exceed max_batch:
  * the call loops over chunks, and from the second chunk on alternates between two lanes: the context's own workspace and
  * a twin (same size, created on first use on the same device, own stream), so that one chunk's latency-bound tail overlaps
  * the next chunk's streaming head.  The environment variable SP_NO_TWIN=1 (read at sp_create) keeps a single lane and a
@@ -148,8 +152,10 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
  *   "xyz" (N x 3 float, levelled+masked)  "normals" (N x 3 float)  "minmax" (6 float)  "voxel_key" (N u32)
  *   "voxel_idx" "h_idx" "v_idx" (int32 pixel indices)   "h_root" "v_root" (int32 per H/V point: smallest
  *   member position of its cluster)   "h_seg_coef" "v_seg_coef" (P x 4 float)  "h_seg_count" "v_seg_count"
- *   "h_seg_idx" "v_seg_idx" (int32 pixel indices, planes concatenated)   "h_hyp" "v_hyp" (int32 x 4 per scored
- *   hypothesis: call id, i0, i1, i2)   "plane_idx" (int32 pixel indices of the final planes, concatenated)
+ *   "h_seg_idx" "v_seg_idx" (int32 pixel indices, planes concatenated)   "h_log" "v_log" (int32 x 10 per RANSAC
+ *   call: cluster, call, n, scored hypotheses, best sample i0 i1 i2, best count, inliers, emitted)
+ *   "h_merge_coef/count/idx" "v_merge_coef/count/idx" (after mergeSeperatedPlanes)
+ *   "plane_idx" (int32 pixel indices of the final planes, concatenated)
  * Returns bytes (sp_tap_bytes), bytes copied (sp_tap_copy) or <0 on error / unknown name. */
 int64_t sp_tap_bytes(sp_ctx *ctx, int frame, const char *name);
 int64_t sp_tap_copy(sp_ctx *ctx, int frame, const char *name, void *dst, int64_t cap);

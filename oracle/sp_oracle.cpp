@@ -951,34 +951,65 @@ int64_t orc_tap_names(orc_ctx *c, char *dst, int64_t cap)
 int orc_stage_ms(orc_ctx *c, double *out, int cap) { int n = std::min(cap, (int)ST_COUNT); for (int i = 0; i < n; ++i) out[i] = c->stage_ms[i]; return n; }
 const char *orc_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 
-/* computeRotationMatrix, /root/reference/test/reader.cpp:228-271.  Eigen::AngleAxisf(angle, axis).toRotationMatrix()
- * for unit axes reduces to the textbook Rx/Ry/Rz with c = cos(angle), s = sin(angle) evaluated in float. */
-static void mat3mul(const float *A, const float *B, float *C)
+/* computeRotationMatrix, /root/reference/test/reader.cpp:228-271, the way Eigen 3 evaluates it in a plain x86-64 (SSE2) build
+ * [Eigen-recall: Geometry/AngleAxis.h, Geometry/Quaternion.h, Geometry/arch/Geometry_SSE.h, Core/arch/SSE/PacketMath.h]:
+ *   - AngleAxisf * AngleAxisf * AngleAxisf is a chain of QUATERNION products, converted to a matrix once;
+ *   - the float quaternion product is the SSE kernel: four lanes (x, y, z, w) of
+ *        (a * b.wwww - a.zxyx * b.yzxx) + (+,+,+,-)(a.yzxz * b.zxyz + a.wwwy * b.xyzy)
+ *   - normalized() divides by sqrt of the SSE2 horizontal sum (c0 + c2) + (c1 + c3) of the squared coefficients.
+ * Written as packet arithmetic over 4-float arrays, unlike the product's scalar form (sp_b200.cu), on purpose. */
+typedef float packet4[4];                                /* coefficient order of Eigen::Quaternionf: x, y, z, w */
+static void swz(const packet4 a, int p, int q, int r, int s, packet4 o) { const float t[4] = { a[p], a[q], a[r], a[s] }; memcpy(o, t, sizeof(t)); }
+static void quat_mul_sse(const packet4 a, const packet4 b, packet4 res)
 {
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
-        C[3 * i + j] = A[3 * i + 0] * B[0 + j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    packet4 a1, b1, a2, b2, a3, b3, bw, s1, s2, lhs;
+    swz(a, 1, 2, 0, 2, a1); swz(b, 2, 0, 1, 2, b1);
+    swz(a, 3, 3, 3, 1, a2); swz(b, 0, 1, 2, 1, b2);
+    swz(a, 2, 0, 1, 0, a3); swz(b, 1, 2, 0, 0, b3);
+    swz(b, 3, 3, 3, 3, bw);
+    for (int i = 0; i < 4; ++i) { s1[i] = a1[i] * b1[i]; s2[i] = a2[i] * b2[i]; }
+    for (int i = 0; i < 4; ++i) { const float m = a[i] * bw[i], n = a3[i] * b3[i]; lhs[i] = m - n; }
+    for (int i = 0; i < 4; ++i) { float t = s1[i] + s2[i]; if (i == 3) t = -t; res[i] = lhs[i] + t; }
+}
+static void quat_to_matrix(const packet4 q, float *m)
+{
+    /* Eigen::QuaternionBase::toRotationMatrix */
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+    const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    m[0] = 1.f - (tyy + tzz); m[1] = txy - twz; m[2] = txz + twy;
+    m[3] = txy + twz; m[4] = 1.f - (txx + tzz); m[5] = tyz - twx;
+    m[6] = txz - twy; m[7] = tyz + twx; m[8] = 1.f - (txx + tyy);
 }
 static void finish_rotation(const float *m2, float *R9)
 {
-    const float m1[9] = { 0, 0, 1, -1, 0, 0, 0, -1, 0 }, m3[9] = { 0, 0, -1, 1, 0, 0, 0, -1, 0 };
-    float t[9]; mat3mul(m3, m2, t); mat3mul(t, m1, R9);
+    /* m3 * m2 * m1 with m1 = [[0,0,1],[-1,0,0],[0,-1,0]], m3 = [[0,0,-1],[1,0,0],[0,-1,0]]: a signed permutation of m2's
+     * entries (every product term is 0 or +-m2(i,j): exact), written out: R(i,j) = sum_k sum_l m3(i,k) m2(k,l) m1(l,j) */
+    R9[0] = m2[7];  R9[1] = m2[8];  R9[2] = -m2[6];
+    R9[3] = -m2[1]; R9[4] = -m2[2]; R9[5] = m2[0];
+    R9[6] = m2[4];  R9[7] = m2[5];  R9[8] = -m2[3];
 }
 void orc_rotation_from_euler(float pitch, float roll, float yaw, float *R9)
 {
-    const float ar = (float)(roll / 180.0 * M_PI), ap = (float)(pitch / 180.0 * M_PI), ay = (float)(yaw / 180.0 * M_PI);
-    const float cr = cosf(ar), sr = sinf(ar), cp = cosf(ap), sp = sinf(ap), cy = cosf(ay), sy = sinf(ay);
-    const float Rx[9] = { 1, 0, 0, 0, cr, -sr, 0, sr, cr }, Ry[9] = { cp, 0, sp, 0, 1, 0, -sp, 0, cp }, Rz[9] = { cy, -sy, 0, sy, cy, 0, 0, 0, 1 };
-    float t[9], m2[9]; mat3mul(Rx, Ry, t); mat3mul(t, Rz, m2);
+    const float ang[3] = { (float)(roll / 180.0 * M_PI), (float)(pitch / 180.0 * M_PI), (float)(yaw / 180.0 * M_PI) };   /* about X, Y, Z */
+    packet4 q[3];
+    for (int k = 0; k < 3; ++k) {
+        const float ha = 0.5f * ang[k], sn = sinf(ha);
+        for (int i = 0; i < 3; ++i) q[k][i] = sn * (i == k ? 1.0f : 0.0f);
+        q[k][3] = cosf(ha);
+    }
+    packet4 t, r;
+    quat_mul_sse(q[0], q[1], t); quat_mul_sse(t, q[2], r);
+    float m2[9]; quat_to_matrix(r, m2);
     finish_rotation(m2, R9);
 }
 void orc_rotation_from_quat(float w, float x, float y, float z, float *R9)
 {
-    const float n = sqrtf(w * w + x * x + y * y + z * z);
-    w /= n; x /= n; y /= n; z /= n;
-    /* Eigen::QuaternionBase::toRotationMatrix */
-    const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z, twx = tx * w, twy = ty * w, twz = tz * w,
-                txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    const float m2[9] = { 1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1.f - (txx + tyy) };
+    packet4 c = { x, y, z, w }, sq;
+    for (int i = 0; i < 4; ++i) sq[i] = c[i] * c[i];
+    const float n = sqrtf((sq[0] + sq[2]) + (sq[1] + sq[3]));
+    for (int i = 0; i < 4; ++i) c[i] = c[i] / n;
+    float m2[9]; quat_to_matrix(c, m2);
     finish_rotation(m2, R9);
 }
 

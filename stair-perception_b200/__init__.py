@@ -197,6 +197,9 @@ class Context:
         if R is not None:
             Rp = _ptr(R)
         fn = self.L.sp_process_frames_device if device_input else self.L.sp_process_frames
+        if device_input and hasattr(clouds, "is_cuda") and clouds.is_cuda:
+            import torch                                     # the library's streams do not know torch's: finish the producer first
+            torch.cuda.current_stream(clouds.device).synchronize()
         self._check(fn(self.h, _ptr(clouds), Rp, nframes, int(show_mode), results.ctypes.data), "sp_process_frames")
         return results
 

@@ -449,33 +449,65 @@ void sp_destroy(sp_ctx *ctx)
     delete ctx;
 }
 
+/* R = m3 * m2 * m1 with the two signed permutations of computeRotationMatrix (test/reader.cpp:233-248): every product
+ * term is 0 or +-m2(i,j), so the result is exact whatever the summation order: R(i,j) = s * m2(p,q). */
+static void sp_wrap_rotation(const float *m2, float *R9)
+{
+    const float m1[9] = { 0, 0, 1, -1, 0, 0, 0, -1, 0 }, m3[9] = { 0, 0, -1, 1, 0, 0, 0, -1, 0 };
+    float u[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) u[3 * i + j] = (m3[3 * i] * m2[j] + m3[3 * i + 1] * m2[3 + j]) + m3[3 * i + 2] * m2[6 + j];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R9[3 * i + j] = (u[3 * i] * m1[j] + u[3 * i + 1] * m1[3 + j]) + u[3 * i + 2] * m1[6 + j];
+}
+
+/* Eigen::QuaternionBase::toRotationMatrix (Geometry/Quaternion.h), coefficient for coefficient */
+static void sp_quat_to_matrix(float w, float x, float y, float z, float *m2)
+{
+    const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z, twx = tx * w, twy = ty * w, twz = tz * w,
+                txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    m2[0] = 1.f - (tyy + tzz); m2[1] = txy - twz; m2[2] = txz + twy;
+    m2[3] = txy + twz; m2[4] = 1.f - (txx + tzz); m2[5] = tyz - twx;
+    m2[6] = txz - twy; m2[7] = tyz + twx; m2[8] = 1.f - (txx + tyy);
+}
+
+/* Eigen's float quaternion product as an x86-64 (SSE2) build evaluates it, Geometry/arch/Geometry_SSE.h [Eigen-recall]:
+ *   res = (a * b.wwww - a.zxyx * b.yzxx) + sign(+,+,+,-) * (a.yzxz * b.zxyz + a.wwwy * b.xyzy)      (lanes x, y, z, w) */
+struct SpQuat { float x, y, z, w; };
+static SpQuat sp_quat_mul(const SpQuat &a, const SpQuat &b)
+{
+    SpQuat r;
+    r.x = (a.x * b.w - a.z * b.y) + (a.y * b.z + a.w * b.x);
+    r.y = (a.y * b.w - a.x * b.z) + (a.z * b.x + a.w * b.y);
+    r.z = (a.z * b.w - a.y * b.x) + (a.x * b.y + a.w * b.z);
+    r.w = (a.w * b.w - a.x * b.x) + -(a.z * b.z + a.y * b.y);
+    return r;
+}
+
 void sp_rotation_from_euler(float pitch, float roll, float yaw, float *R9)
 {
-    /* m2 = Rx(roll) * Ry(pitch) * Rz(yaw); angles = v / 180.0 * M_PI in double, narrowed (reader.cpp:240-242) */
+    /* m2 = AngleAxisf(roll, X) * AngleAxisf(pitch, Y) * AngleAxisf(yaw, Z) (reader.cpp:240-242).  Eigen evaluates a product of
+     * AngleAxis objects as QUATERNION products ((qx * qy) * qz, AngleAxis::operator*) and converts once (Matrix3f = RotationBase
+     * -> toRotationMatrix).  Angles: v / 180.0 * M_PI in double, narrowed by the AngleAxisf constructor; the quaternion of an
+     * AngleAxis is (cos(angle / 2), sin(angle / 2) * axis) in float (QuaternionBase::operator=(AngleAxis)). */
     const float ar = (float)(roll / 180.0 * M_PI), ap = (float)(pitch / 180.0 * M_PI), ay = (float)(yaw / 180.0 * M_PI);
-    const float cr = cosf(ar), sr = sinf(ar), cp = cosf(ap), sp = sinf(ap), cy = cosf(ay), sy = sinf(ay);
-    const float Rx[9] = { 1, 0, 0, 0, cr, -sr, 0, sr, cr }, Ry[9] = { cp, 0, sp, 0, 1, 0, -sp, 0, cp }, Rz[9] = { cy, -sy, 0, sy, cy, 0, 0, 0, 1 };
-    auto mul = [](const float *A, const float *Bm, float *C) {
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * Bm[j] + A[3 * i + 1] * Bm[3 + j] + A[3 * i + 2] * Bm[6 + j];
-    };
-    const float m1[9] = { 0, 0, 1, -1, 0, 0, 0, -1, 0 }, m3[9] = { 0, 0, -1, 1, 0, 0, 0, -1, 0 };
-    float t[9], m2[9], u[9];
-    mul(Rx, Ry, t); mul(t, Rz, m2); mul(m3, m2, u); mul(u, m1, R9);
+    const float hr = 0.5f * ar, hp = 0.5f * ap, hy = 0.5f * ay;
+    const SpQuat qx = { sinf(hr) * 1.f, sinf(hr) * 0.f, sinf(hr) * 0.f, cosf(hr) };
+    const SpQuat qy = { sinf(hp) * 0.f, sinf(hp) * 1.f, sinf(hp) * 0.f, cosf(hp) };
+    const SpQuat qz = { sinf(hy) * 0.f, sinf(hy) * 0.f, sinf(hy) * 1.f, cosf(hy) };
+    const SpQuat q = sp_quat_mul(sp_quat_mul(qx, qy), qz);
+    float m2[9];
+    sp_quat_to_matrix(q.w, q.x, q.y, q.z, m2);
+    sp_wrap_rotation(m2, R9);
 }
 
 void sp_rotation_from_quat(float w, float x, float y, float z, float *R9)
 {
-    const float n = sqrtf(w * w + x * x + y * y + z * z);
+    /* quaternionf.normalized() (reader.cpp:267): coeffs() / norm(), norm = sqrt of the packet reduction of the squares in
+     * coefficient order (x, y, z, w): SSE2 predux = (x2 + z2) + (y2 + w2) [Eigen-recall, Core/arch/SSE/PacketMath.h] */
+    const float n = sqrtf((x * x + z * z) + (y * y + w * w));
     w /= n; x /= n; y /= n; z /= n;
-    const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z, twx = tx * w, twy = ty * w, twz = tz * w,
-                txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    const float m2[9] = { 1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1.f - (txx + tyy) };
-    auto mul = [](const float *A, const float *Bm, float *C) {
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * Bm[j] + A[3 * i + 1] * Bm[3 + j] + A[3 * i + 2] * Bm[6 + j];
-    };
-    const float m1[9] = { 0, 0, 1, -1, 0, 0, 0, -1, 0 }, m3[9] = { 0, 0, -1, 1, 0, 0, 0, -1, 0 };
-    float u[9];
-    mul(m3, m2, u); mul(u, m1, R9);
+    float m2[9];
+    sp_quat_to_matrix(w, x, y, z, m2);
+    sp_wrap_rotation(m2, R9);
 }
 
 /* the twin lane of a context (created on first use; a batch that does not get one simply runs on a single lane) */
@@ -537,6 +569,19 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         }
         return SP_OK;
     };
+    /* an error in the middle of a batch must not leave copies in flight on the caller's buffers: every exit of the chunk loop
+     * goes through `settle`, which drains the copy stream and the lanes and forgets the half-finished chunk */
+    auto settle = [&](int rc) -> int {
+        if (rc != SP_OK) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            for (int l = 0; l < nl; ++l) cudaStreamSynchronize(lanes[l]->stream);
+            (void)cudaGetLastError();
+            ctx->last = nullptr;
+            for (int l = 0; l < nl; ++l) lanes[l]->last_nB = 0;
+        }
+        return rc;
+    };
+    auto run_batch = [&]() -> int {
     if (host_in && nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
@@ -567,6 +612,8 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         collect_times(ctx->last);
     }
     return SP_OK;
+    };
+    return settle(run_batch());
 }
 
 int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, const uint8_t *bgrx, const sp_intrinsics *K, int mirror,
@@ -623,6 +670,17 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         return SP_OK;
     };
     int buf = 0;
+    auto settle = [&](int rc) -> int {                       /* as in process_impl: no copy stays in flight after an error */
+        if (rc != SP_OK) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            for (int l = 0; l < nl; ++l) cudaStreamSynchronize(lanes[l]->stream);
+            (void)cudaGetLastError();
+            ctx->last = nullptr;
+            for (int l = 0; l < nl; ++l) lanes[l]->last_nB = 0;
+        }
+        return rc;
+    };
+    auto run_batch = [&]() -> int {
     if (nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
         const int f0 = ci * ctx->B, nB = std::min(ctx->B, nframes - f0);
@@ -650,6 +708,8 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         collect_times(ctx->last);
     }
     return SP_OK;
+    };
+    return settle(run_batch());
 }
 
 int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results)

@@ -706,7 +706,11 @@ __global__ void __launch_bounds__(MG_WARPS * 32) k_merge(SpDev d, int nB)
             if (lane < 20) {
                 const int r = d.rnd[(rpos + lane) & (SP_RAND_LEN - 1)];
                 const int pi = mg_point(d, s, chunks, nxt, mp[i].head, r % np);
-                const float4 pw = PT[pi];
+                /* the reference indexes points[rand() % number-of-planes] (StairPerception.cpp:985): past the end of a plane with
+                 * fewer points than there are planes (only possible when seg_rest_point < plane count) it reads out of bounds.
+                 * Here: a NaN sample, which never counts as near, and a capacity flag on the frame. */
+                float4 pw = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), 0.f);
+                if (pi >= 0) pw = PT[pi]; else atomicOr(&d.flags[f], 8);
                 S.sx[i][lane] = pw.x; S.sy[i][lane] = pw.y; S.sz[i][lane] = pw.z;
             }
             rpos += 20;

@@ -64,6 +64,20 @@ def test_host_rotation_entry_points_match_oracle(sp, orc):
         assert np.array_equal(sp.rotation_from_quat(*q), orc.rotation_from_quat(*q))
         R = sp.rotation_from_quat(*q).reshape(3, 3).astype(np.float64)
         assert np.allclose(R @ R.T, np.eye(3), atol=1e-5) and abs(np.linalg.det(R) - 1) < 1e-5
+        # a check that shares no restatement with the oracle: the double-precision closed forms of test/reader.cpp:233-271
+        a = np.deg2rad([r, p, y])
+        Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+        Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+        Rz = np.array([[np.cos(a[2]), -np.sin(a[2]), 0], [np.sin(a[2]), np.cos(a[2]), 0], [0, 0, 1]])
+        m1 = np.array([[0, 0, 1], [-1, 0, 0], [0, -1, 0]])
+        m3 = np.array([[0, 0, -1], [1, 0, 0], [0, -1, 0]])
+        assert np.allclose(sp.rotation_from_euler(p, r, y).reshape(3, 3), m3 @ Rx @ Ry @ Rz @ m1, rtol=0, atol=5e-7)
+        qn = q / np.linalg.norm(q)
+        w, x, yy, z = qn
+        M = np.array([[1 - 2 * (yy * yy + z * z), 2 * (x * yy - z * w), 2 * (x * z + yy * w)],
+                      [2 * (x * yy + z * w), 1 - 2 * (x * x + z * z), 2 * (yy * z - x * w)],
+                      [2 * (x * z - yy * w), 2 * (yy * z + x * w), 1 - 2 * (x * x + yy * yy)]])
+        assert np.allclose(R, m3 @ M @ m1, rtol=0, atol=5e-7)
 
 
 @pytest.mark.skipif(has_cuda(), reason="checks the no-GPU behaviour")
