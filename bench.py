@@ -3,11 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step = one pass of the whole front-end (levelling .. sorted plane records) over this rank's batch of frames.
-`value`  : device-resident input (HBM), includes the D2H of the per-frame plane records and, for N > 1, the gather.  The
-           library runs the chunks of a batch on two lanes (context + twin workspace), see DESIGN.md section 2.
-`e2e`    : the same metric through sp_process_frames with pinned HOST buffers (H2D + D2H inside the timed region).
-`roofline`: the fused ingest+normals kernel (K1K2) timed with CUDA events on the library's stream.
+A step = one pass of the whole front-end (levelling .. sorted plane records) over ONE batch of 8192 frames (BASELINE.json config 5),
+sharded frame-wise across the N GPUs (stair-perception_b200/shard.py): STRONG scaling.  Every GPU runs whole frames; the only
+exchange is the all-gather of the compact plane records (64-byte header + n_planes x 224 B per frame), device to device.
+`value`  : the batch resident in HBM; the step ends with the gathered records of all 8192 frames in host memory on every rank.
+           The library runs the chunks of a rank's block on two lanes (context + twin workspace), see DESIGN.md section 2.
+`e2e`    : the same step from pinned HOST clouds (H2D of every cloud and D2H of the records inside the timed region).
+`roofline`: the fused ingest+normals kernel (K1K2) timed alone with CUDA events on the library's stream.
+`config4`, `latency_b1` (N = 1): the dense 2 M-point kNN scene and the reference's own one-frame-per-call mode.
 `cpu_baseline` / `--impl reference`: the CPU oracle (a port: the reference's PCL build cannot be compiled in this
 image) on the box's host cores, on a bounded sample of the same synthetic frames.
 """
@@ -27,7 +30,7 @@ sys.path.insert(0, ROOT)
 W, H = 512, 424
 N = W * H
 K1K2_BYTES_PER_POINT = 16 + 12 + 12          # read xyzrgba, write levelled xyz + normals (fused K1+K2); the kernel stores both as float4 (48 B moved)
-N_DISTINCT = 32                              # distinct synthetic frames; the batch tiles them
+N_DISTINCT = 256                             # distinct synthetic frames (seeds 0..255); the 8192-frame batch cycles through them
 
 
 def host_cores():
@@ -68,15 +71,18 @@ def bind_to_gpu_numa_node(index):
 
 
 def load_traffic(kernel, frames_per_launch):
-    """dram bytes of one launch from the committed ncu capture (profiles/r01_traffic.json), or None"""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(p) as f:
-            t = json.load(f)
-        if t["kernel"] == kernel and int(t["frames_per_launch"]) == int(frames_per_launch):
-            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
-    except Exception:
-        pass
+    """DRAM bytes of one launch of `kernel` from the newest committed ncu --set full capture (profiles/r*_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum); ncu cannot run inside the timed run, so the line says which capture"""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            with open(p) as f:
+                t = json.load(f)
+            if t["kernel"] == kernel and int(t["frames_per_launch"]) == int(frames_per_launch):
+                return {"bytes": int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]),
+                        "source": "%s (%s)" % (os.path.basename(p), t.get("captured", "round 1 capture"))}
+        except Exception:
+            pass
     return None
 
 
@@ -131,12 +137,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_frames(n):
-    from __graft_entry__ import load_package
-    load_package()
+def _one_frame(i):
     import importlib
     synth = importlib.import_module("stair_perception_b200.synth")
-    return synth.make_batch(n)
+    return synth.make_frame(i)
+
+
+def make_frames(n, workers=1):
+    """frames 0 .. n-1 of the seeded synthetic generator (identical on every rank); a fork pool when the host has the cores
+    (call it before CUDA is initialised)"""
+    from __graft_entry__ import load_package
+    load_package()
+    if workers > 1 and n > 8:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            out = pool.map(_one_frame, range(n), chunksize=max(1, n // (4 * workers)))
+    else:
+        out = [_one_frame(i) for i in range(n)]
+    return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
 
 
 def cpu_baseline(sp, recs, Rs, seconds_budget=12.0):
@@ -175,7 +193,7 @@ def cpu_baseline(sp, recs, Rs, seconds_budget=12.0):
         single = {"error": str(e)}
     return {"value": frames / dt, "unit": "frames/s", "cores": nthreads, "kind": "port",
             "sample": "%d synthetic 512x424 stair frames x %d passes, oracle/liborc.so, one frame per thread, %d threads" % (n, reps, nthreads),
-            "single_core": single}
+            "build": orc.build_flags(), "single_core": single}
 
 
 def run_reference(args):
@@ -188,7 +206,7 @@ def run_reference(args):
     from oracle import orc
     orc.build()
     cores = host_cores()
-    n = max(8, min(N_DISTINCT, cores))
+    n = max(8, min(32, cores))
     recs, Rs = make_frames(n)
     passes = 8                                                  # one step = 8 passes over the distinct frames (about half a second of CPU work)
     for _ in range(max(0, args.warmup)):
@@ -202,13 +220,86 @@ def run_reference(args):
     sample = "%d synthetic 512x424 stair frames x %d passes per step, CPU oracle port (oracle/liborc.so), %d host threads" % (n, passes, cores)
     line = {"impl": "reference", "metric": "frames/sec of 512x424 stair clouds through segmentation; % HBM roofline", "value": val, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 5: batch of synthetic Kinect-V2 4-step stair frames, 512x424 (217088 pts), levelling + full segmentation front-end",
-                       "sample": "bounded sample of the 8192-frame batch", "frames_per_step": n * passes},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config 5: batch of 8192 synthetic Kinect-V2 4-step stair frames, 512x424 (217088 pts), levelling + full segmentation front-end",
+                       "sample": "bounded sample of the 8192-frame batch (the CPU arm's throughput does not depend on the batch length)", "frames_per_step": n * passes},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, "build": orc.build_flags()},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+def bench_config4(sp, dev, peak):
+    """BASELINE.json config 4: the dense 2 M-point unorganised scene (leaf 0.005, kNN normals, k = 69), one frame per call,
+    device-resident input.  Roofline of k_knn_normals on both bases of SURVEY 8(d): compulsory 24 B/point (16 in, 12 out: the
+    neighbours come from L2) and gather-inclusive 852 B/point (k x 12 B of neighbour coordinates + 24)."""
+    import importlib
+    import torch
+    synth = importlib.import_module("stair_perception_b200.synth")
+    n_points = 2_000_000
+    rec = synth.make_dense_scene(n_points, seed=0)
+    p = dict(sp.DEFAULT_PARAMS)
+    p.update(synth.DENSE_PARAMS)
+    ctx = sp.Context(p, device=dev.index, width=n_points, height=1, max_batch=1)
+    ctx.set_normal_mode(1)
+    d_rec = torch.from_numpy(rec.view(np.uint8).reshape(1, -1)).to(dev)
+    torch.cuda.synchronize()
+    res = np.zeros(1, dtype=sp.FRAME_DTYPE)
+    for _ in range(3):
+        ctx.process_frames(d_rec, None, device_input=True, nframes=1, results=res)
+    t0 = time.perf_counter()
+    reps = 8
+    for _ in range(reps):
+        ctx.process_frames(d_rec, None, device_input=True, nframes=1, results=res)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    ctx.set_trace(True)
+    ctx.process_frames(d_rec, None, device_input=True, nframes=1, results=res)
+    tr = ctx.trace_ms()
+    ctx.set_trace(False)
+    knn_ms = dict(tr).get("k_knn_normals", 0.0)
+    n_valid = int(res[0]["n_valid"])
+    out = {"workload": "config 4: dense 2 M-point unorganised stair scene, leaf 0.005, kNN normals (k = %d), one frame per call" % p["normal_compute_points"],
+           "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "points_per_s": n_points * 1e3 / ms, "n_planes": int(res[0]["n_planes"]),
+           "kernels": [{"kernel": k, "ms": round(t, 4)} for k, t in sorted(tr, key=lambda kv: -kv[1])[:6]]}
+    if knn_ms > 0:
+        k = int(p["normal_compute_points"])
+        for name, bpp in (("compulsory", 24), ("with_neighbour_gathers", 24 + 12 * k)):
+            ach = bpp * n_valid / (knn_ms * 1e-3) / 1e9
+            out["roofline_knn_" + name] = {"bound": "hbm", "kernel": "k_knn_normals", "bytes_per_point": bpp, "achieved": ach, "peak": peak,
+                                           "unit": "GB/s", "frac": ach / peak, "ms_per_launch": knn_ms, "points": n_valid}
+    ctx.close()
+    return out
+
+
+def bench_latency_b1(sp, dev, recs, Rs):
+    """The reference's own mode of use: one frame per call (test/processor.cpp:156-174), host cloud in, host record out, through
+    sp_process_frames on a max_batch = 1 context; median over 30 calls after 5 warm-up calls.  Beside it: the published 137 ms
+    (pic/screenshot1.png, unknown CPU) and the oracle's single-core time in cpu_baseline.single_core."""
+    ctx = sp.Context(device=dev.index, width=W, height=H, max_batch=1)
+    out = {"published_reference_ms": 137.0, "api": "sp_process_frames, max_batch = 1, pageable host cloud -> host record"}
+    cases = [("synthetic_frame_0", recs[0], Rs[0].reshape(1, 9))]
+    pcd = os.path.join(ROOT, "tests", "golden", "samples", "0001_cloud.pcd")
+    if os.path.exists(pcd):
+        rec, w, h = sp.read_pcd(pcd)
+        cases.append(("samples_0001", rec, None))
+    for name, rec, R in cases:
+        for _ in range(5):
+            ctx.process_frames(rec, R)
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            r = ctx.process_frames(rec, R)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        t1 = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            ctx.process_frames(rec, R)
+            ctx.stair_model(0)
+            t1.append((time.perf_counter() - t0) * 1e3)
+        out[name] = {"ms_median": float(np.median(ts)), "ms_min": float(np.min(ts)), "ms_with_stair_model_median": float(np.median(t1)),
+                     "n_planes": int(r[0]["n_planes"])}
+    ctx.close()
+    return out
 
 
 def main():
@@ -217,10 +308,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--frames", type=int, default=8192, help="frames per GPU per step (config 5: 8192)")
-    ap.add_argument("--e2e-frames", type=int, default=4096, help="frames per GPU per end-to-end step (pinned host input, 14.2 GB)")
+    ap.add_argument("--frames", type=int, default=8192, help="frames of the WHOLE batch per step (config 5: 8192), sharded frame-wise across the GPUs")
+    ap.add_argument("--e2e-frames", type=int, default=8192, help="frames of the whole batch per end-to-end step (pinned host input, 28.5 GB over all ranks)")
     ap.add_argument("--max-batch", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip config 4, single-frame latency, the weak-scaling figure and the depth-image leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -231,14 +323,19 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the distinct frames first (fork pool, before CUDA exists in this process); identical on every rank (seeded)
+    recs, Rs = make_frames(N_DISTINCT, workers=max(1, min(32, host_cores() // max(1, world))))
+
+    import importlib
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
     sp = load_package()
+    shard = importlib.import_module("stair_perception_b200.shard")
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -250,39 +347,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    # ---- the batch: frame i of the 8192 = distinct frame i % 256; this rank holds (and runs) its contiguous block ---------------
     F = args.frames
-    recs, Rs = make_frames(N_DISTINCT)                         # identical on every rank (seeded)
+    lo, hi = shard.shard_bounds(F, rank, world)
+    Fl = hi - lo
     base = torch.from_numpy(recs.view(np.uint8).reshape(N_DISTINCT, N * 16)).to(dev)
-    reps = (F + N_DISTINCT - 1) // N_DISTINCT
-    d_clouds = base.repeat(reps, 1)[:F].contiguous()           # F x 3.47 MB resident in HBM (>> L2)
-    d_R = torch.from_numpy(Rs).to(dev).repeat(reps, 1)[:F].contiguous()
-    del base
-    Fe = min(args.e2e_frames, F, max(256, 8192 // world))      # pinned host memory: 14 GB at N=1, 3.6 GB per rank at N=8
-    h_clouds = torch.empty((Fe, N * 16), dtype=torch.uint8).pin_memory()
-    h_R = torch.empty((Fe, 9), dtype=torch.float32).pin_memory()
-    base_h = torch.from_numpy(recs.view(np.uint8).reshape(N_DISTINCT, N * 16))
-    R_h = torch.from_numpy(Rs)
-    for i0 in range(0, Fe, N_DISTINCT):                        # tile the distinct frames without a 14 GB temporary
-        n = min(N_DISTINCT, Fe - i0)
-        h_clouds[i0:i0 + n].copy_(base_h[:n])
-        h_R[i0:i0 + n].copy_(R_h[:n])
+    base_R = torch.from_numpy(Rs).to(dev)
+    idx = (torch.arange(lo, hi, device=dev) % N_DISTINCT)
+    d_clouds = base.index_select(0, idx).contiguous()          # Fl x 3.47 MB resident in HBM (>> L2)
+    d_R = base_R.index_select(0, idx).contiguous()
     torch.cuda.synchronize()
 
     ctx = sp.Context(device=local, width=W, height=H, max_batch=args.max_batch)
-    results = np.zeros(F, dtype=sp.FRAME_DTYPE)
-    res_e = np.zeros(Fe, dtype=sp.FRAME_DTYPE)
-    gather_buf = None
-    if world > 1:
-        gather_buf = torch.empty((world, F * sp.FRAME_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    cap = int(sp.lib().sp_compact_bytes_max(shard.shard_sizes(F, world)[0]))
+    cbuf = torch.empty(cap, dtype=torch.uint8, device=dev)     # this rank's compact records (device)
+    h_all = torch.empty(int(sp.lib().sp_compact_bytes_max(F)), dtype=torch.uint8, pin_memory=True)   # the whole batch's, on the host
+    last = {}
 
     def step_device():
-        ctx.process_frames(d_clouds, d_R, device_input=True, nframes=F, results=results)
-        if world > 1:   # gather of the per-frame plane records (the only inter-GPU exchange of this path)
-            mine = torch.from_numpy(results.view(np.uint8)).to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gather_buf.view(-1), mine)
-
-    def step_e2e():
-        ctx.process_frames(h_clouds, h_R, device_input=False, nframes=Fe, results=res_e)
+        # shard -> whole frames on this GPU, records stay on the device -> all-gather of the compact records -> host
+        _, nb = ctx.process_frames_compact(d_clouds, d_R, device_input=True, nframes=Fl, out=cbuf)
+        last["packed"], last["sizes"] = shard.gather_compact(cbuf, nb, host_out=h_all)
 
     def barrier():
         torch.cuda.synchronize()
@@ -301,7 +386,7 @@ def main():
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         ms = max(e0.elapsed_time(e1), 0.0)
-        ms = max(ms, wall * 0.999) if ms < wall * 0.5 else ms     # the library syncs its own stream inside fn
+        ms = max(ms, wall * 0.999) if ms < wall * 0.5 else ms     # the library syncs its own streams inside fn
         barrier()
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -318,13 +403,23 @@ def main():
     launches = ctx.launch_count() - l0
     stage_full = ctx.stage_ms()
     clocks = sampler.stop() if rank == 0 else None
-    value = F * world * args.steps / (ms / 1e3)
+    value = F * args.steps / (ms / 1e3)
+    # what came back: every frame of the batch, in batch order, on every rank
+    results = sp.expand_compact(last["packed"], F)
+    assert int(results["n_planes"].min()) >= 1 and int(results["status"].max()) == 0, "unexpected empty results"
+    assert np.array_equal(results[:N_DISTINCT].view(np.uint8), results[N_DISTINCT:2 * N_DISTINCT].view(np.uint8)) or F < 2 * N_DISTINCT
+    # the exchange alone (sizes + compact records + copy to the host), device-timed
+    gather_ms = None
+    if world > 1:
+        _, nb = ctx.process_frames_compact(d_clouds, d_R, device_input=True, nframes=Fl, out=cbuf)
+        gather_ms = timed(lambda: shard.gather_compact(cbuf, nb, host_out=h_all), 5) / 5
 
     # the dominant streaming kernel alone (K1K2 = ingest + levelling + masking + organised normals), CUDA events on its stream
-    nb = args.max_batch
+    nb = min(args.max_batch, Fl)
     k_ms = []
     for i in range(3 + 10):
-        ctx.run_stage_device(d_clouds.data_ptr() + (i % max(1, F // nb)) * nb * N * 16, d_R.data_ptr(), nb, 0)
+        off = (i % max(1, Fl // nb)) * nb
+        ctx.run_stage_device(d_clouds.data_ptr() + off * N * 16, d_R.data_ptr() + off * 36, nb, 0)
         t = ctx.stage_ms()["ingest_normals"]
         if i >= 3:
             k_ms.append(t)
@@ -337,90 +432,161 @@ def main():
         if i >= 2:
             vox_ms.append(ctx.stage_ms()["voxel"])
     # per-kernel times of one chunk (the library's own trace: a CUDA event after every launch on its stream), outside any timed region
+    res_nb = np.zeros(nb, dtype=sp.FRAME_DTYPE)
     ctx.set_trace(True)
-    ctx.process_frames(d_clouds, d_R, device_input=True, nframes=nb, results=results[:nb])
+    ctx.process_frames(d_clouds, d_R, device_input=True, nframes=nb, results=res_nb)
     trace = ctx.trace_ms()
     ctx.set_trace(False)
     chunk_ms = sum(t for _, t in trace)
     # the voxel stage's streaming kernel: reads every levelled point (16 B), writes (key, pixel) = 8 B per cropped point
-    tdict = dict(trace)
-    n_crop = int(results[:nb]["n_crop"].sum())
-    vk_bytes = 16 * N * nb + 8 * n_crop
-    vk_ms = tdict.get("k_voxel_key", 0.0)
+    tdict = {}
+    for k, t in trace:
+        tdict[k] = tdict.get(k, 0.0) + t
+    n_crop = int(res_nb["n_crop"].sum())
+    n_vox = int(res_nb["n_voxel"].sum())
     roof_voxel = None
+    vk_ms = tdict.get("k_voxel_key", 0.0)
     if vk_ms > 0:
+        vk_bytes = 16 * N * nb + 8 * n_crop
         roof_voxel = {"bound": "hbm", "kernel": "k_voxel_key", "achieved": vk_bytes / (vk_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                       "frac": vk_bytes / (vk_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vk_ms, "algorithmic_bytes_per_launch": vk_bytes,
                       "note": "timed inside a traced chunk (one CUDA event before and after the launch on the library's stream)"}
-    kernels = [{"kernel": k, "ms": round(t, 4), "share": round(t / max(chunk_ms, 1e-9), 4)} for k, t in sorted(trace, key=lambda kv: -kv[1])[:8]]
+    # the whole voxel stage against its compulsory bytes (12 B per point read + 4 B per voxel written)
+    vstage_ms = float(np.mean(vox_ms))
+    vs_bytes = 12 * N * nb + 4 * n_vox
+    roof_vstage = {"bound": "hbm", "kernel": "voxel stage (grid + key + sort + pick + lists)", "achieved": vs_bytes / (vstage_ms * 1e-3) / 1e9, "peak": peak,
+                   "unit": "GB/s", "frac": vs_bytes / (vstage_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vstage_ms, "algorithmic_bytes_per_launch": vs_bytes}
+    kernels = [{"kernel": k, "ms": round(t, 4), "share": round(t / max(chunk_ms, 1e-9), 4)} for k, t in sorted(tdict.items(), key=lambda kv: -kv[1])[:10]]
+
+    # ---- end to end: the same batch from pinned HOST memory (H2D of the clouds and D2H of the records inside the timed region) ----
+    Fe = min(args.e2e_frames, F)
+    elo, ehi = shard.shard_bounds(Fe, rank, world)
+    Fel = ehi - elo
+    try:
+        h_clouds = torch.empty((Fel, N * 16), dtype=torch.uint8, pin_memory=True)
+    except RuntimeError:                                       # not enough lockable host memory for 28.5 GB: half the batch
+        Fe = Fe // 2
+        elo, ehi = shard.shard_bounds(Fe, rank, world)
+        Fel = ehi - elo
+        h_clouds = torch.empty((Fel, N * 16), dtype=torch.uint8, pin_memory=True)
+    h_R = torch.empty((Fel, 9), dtype=torch.float32, pin_memory=True)
+    base_h = torch.from_numpy(recs.view(np.uint8).reshape(N_DISTINCT, N * 16))
+    R_h = torch.from_numpy(Rs)
+    for i in range(Fel):
+        h_clouds[i].copy_(base_h[(elo + i) % N_DISTINCT])
+        h_R[i].copy_(R_h[(elo + i) % N_DISTINCT])
+
+    def step_e2e():
+        _, nbytes = ctx.process_frames_compact(h_clouds, h_R, device_input=False, nframes=Fel, out=cbuf)
+        last["packed_e"], _ = shard.gather_compact(cbuf, nbytes, host_out=h_all)
 
     for _ in range(3):
         step_e2e()
     ms_e = timed(step_e2e, args.steps)
-    e2e_val = Fe * world * args.steps / (ms_e / 1e3)
+    e2e_val = Fe * args.steps / (ms_e / 1e3)
+    res_e = sp.expand_compact(last["packed_e"], Fe)
+    assert np.array_equal(res_e.view(np.uint8), results[:Fe].view(np.uint8)), "host-input records differ from device-input records"
+    d2h_e = int(last["packed_e"].size)
 
-    # the same frames entering as what the sensor delivers (uint16 depth in mm + registered colour, 6 B / pixel instead of 16):
-    # sp_process_depth_frames back-projects on the device (K2G::updateCloud), everything else is identical
-    import importlib
-    synth = importlib.import_module("stair_perception_b200.synth")
-    dframes = [synth.make_depth_frame(i) for i in range(N_DISTINCT)]
-    h_depth = torch.empty((Fe, H, W), dtype=torch.uint16).pin_memory()
-    h_bgrx = torch.empty((Fe, H, W, 4), dtype=torch.uint8).pin_memory()
-    for i in range(Fe):
-        h_depth[i].copy_(torch.from_numpy(dframes[i % N_DISTINCT][0]))
-        h_bgrx[i].copy_(torch.from_numpy(dframes[i % N_DISTINCT][1]))
-    res_d = np.zeros(Fe, dtype=sp.FRAME_DTYPE)
+    extras = {}
+    if not args.no_extras:
+        # weak scaling for reference next to the strong figure: every GPU runs the whole 8192-frame batch (no exchange)
+        if world > 1:
+            del d_clouds
+            torch.cuda.empty_cache()
+            idx = (torch.arange(0, F, device=dev) % N_DISTINCT)
+            d_all = base.index_select(0, idx).contiguous()
+            d_Rall = base_R.index_select(0, idx).contiguous()
+            cbig = torch.empty(int(sp.lib().sp_compact_bytes_max(F)), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
 
-    def step_depth():
-        ctx.process_depth_frames(h_depth, synth.INTRINSICS, bgrx=h_bgrx, mirror=True, R=h_R, nframes=Fe, results=res_d)
+            def step_weak():
+                ctx.process_frames_compact(d_all, d_Rall, device_input=True, nframes=F, out=cbig)
 
-    for _ in range(3):
-        step_depth()
-    ms_d = timed(step_depth, args.steps)
-    depth_val = Fe * world * args.steps / (ms_d / 1e3)
-    assert int(res_d["n_planes"].min()) >= 1 and int(res_d["status"].max()) == 0
+            step_weak()
+            ms_w = timed(step_weak, 2)
+            extras["weak_scaling"] = {"value": F * world * 2 / (ms_w / 1e3), "unit": "frames/s", "frames_per_gpu_per_step": F, "ms_per_step": ms_w / 2,
+                                      "note": "every GPU runs its own 8192-frame batch, no exchange (round 1's figure)"}
+            del d_all, cbig
+            torch.cuda.empty_cache()
+        # the same frames entering as what the sensor delivers (uint16 depth in mm + registered colour, 6 B / pixel instead of 16):
+        # sp_process_depth_frames back-projects on the device (K2G::updateCloud), everything else is identical
+        synth = importlib.import_module("stair_perception_b200.synth")
+        Fd = min(4096, Fe)
+        dlo, dhi = shard.shard_bounds(Fd, rank, world)
+        Fdl = dhi - dlo
+        nd = min(32, N_DISTINCT)
+        dframes = [synth.make_depth_frame(i) for i in range(nd)]
+        h_depth = torch.empty((Fdl, H, W), dtype=torch.uint16, pin_memory=True)
+        h_bgrx = torch.empty((Fdl, H, W, 4), dtype=torch.uint8, pin_memory=True)
+        h_Rd = torch.empty((Fdl, 9), dtype=torch.float32, pin_memory=True)
+        for i in range(Fdl):
+            h_depth[i].copy_(torch.from_numpy(dframes[(dlo + i) % nd][0]))
+            h_bgrx[i].copy_(torch.from_numpy(dframes[(dlo + i) % nd][1]))
+            h_Rd[i].copy_(torch.from_numpy(dframes[(dlo + i) % nd][2]))
+        res_d = np.zeros(Fdl, dtype=sp.FRAME_DTYPE)
 
-    # sanity: the batch really produced planes
-    assert int(results["n_planes"].min()) >= 1 and int(results["status"].max()) == 0, "unexpected empty results"
+        def step_depth():
+            ctx.process_depth_frames(h_depth, synth.INTRINSICS, bgrx=h_bgrx, mirror=True, R=h_Rd, nframes=Fdl, results=res_d)
+
+        for _ in range(2):
+            step_depth()
+        ms_d = timed(step_depth, args.steps)
+        assert int(res_d["n_planes"].min()) >= 1 and int(res_d["status"].max()) == 0
+        extras["e2e_depth_input"] = {"value": Fd * args.steps / (ms_d / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(Fd * (N * 6 + 36)),
+                                     "d2h_bytes_per_step": int(Fd * sp.FRAME_DTYPE.itemsize), "frames_per_step": Fd, "ms_per_step": ms_d / args.steps,
+                                     "note": "%d distinct scenes entering as uint16 depth + registered colour (6 B/pixel) through sp_process_depth_frames, "
+                                             "sharded like the batch, fixed-size records to the host, no exchange" % nd}
+        del h_depth, h_bgrx
+        if rank == 0 and world == 1:
+            extras["config4"] = bench_config4(sp, dev, peak)
+            extras["latency_b1"] = bench_latency_b1(sp, dev, recs, Rs)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(sp, recs[:max(8, min(N_DISTINCT, host_cores()))], Rs[:max(8, min(N_DISTINCT, host_cores()))])
+        nc = max(8, min(32, host_cores()))
+        cpu = cpu_baseline(sp, recs[:nc], Rs[:nc])
 
     if rank == 0:
+        traffic = load_traffic("k_ingest_normals", nb)
         line = {
             "metric": "frames/sec of 512x424 stair clouds through segmentation; % HBM roofline",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 5: batch of synthetic Kinect-V2 4-step stair frames, 512x424 (217088 pts), levelling + full segmentation front-end",
-                       "frames_per_gpu_per_step": F, "distinct_frames": N_DISTINCT, "max_batch": args.max_batch,
+            "config": {"workload": "config 5: batch of 8192 synthetic Kinect-V2 4-step stair frames, 512x424 (217088 pts), levelling + full segmentation front-end",
+                       "frames_per_step": F, "frames_per_gpu_per_step": Fl, "distinct_frames": N_DISTINCT, "max_batch": args.max_batch,
                        "lanes": 1 if os.environ.get("SP_NO_TWIN", "") not in ("", "0") else 2,
-                       "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (F * N * 16 / 1e9), "parallelism": "frames sharded across %d GPU(s)" % world,
+                       "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (Fl * N * 16 / 1e9),
+                       "parallelism": "ONE %d-frame batch sharded frame-wise across %d GPU(s) (shard.shard_bounds), whole frames per GPU, "
+                                      "all-gather of the compact plane records only (shard.gather_compact)" % (F, world),
+                       "api": "sp_process_frames_compact (records stay on the device until the exchange) + one D2H of the gathered records",
                        "host_numa_binding": numa_node},
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 16 + 36)),
-                    "d2h_bytes_per_step": int(Fe * sp.FRAME_DTYPE.itemsize), "frames_per_gpu_per_step": Fe, "ms_per_step": ms_e / args.steps},
-            "e2e_depth_input": {"value": depth_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 6 + 36)),
-                                "d2h_bytes_per_step": int(Fe * sp.FRAME_DTYPE.itemsize), "frames_per_gpu_per_step": Fe, "ms_per_step": ms_d / args.steps,
-                                "note": "same scenes entering as uint16 depth + registered colour (6 B/pixel) through sp_process_depth_frames"},
+                    "d2h_bytes_per_step": d2h_e, "frames_per_step": Fe, "ms_per_step": ms_e / args.steps,
+                    "api": "sp_process_frames_compact from pinned host clouds (H2D inside), exchange, compact records to the host (D2H inside)"},
+            "gather": {"ms": gather_ms, "bytes_per_rank": [int(v) for v in last["sizes"]],
+                       "note": "sizes all-gather + padded all-gather of the compact records (NCCL, device buffers) + concatenation + D2H, device-timed"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_ingest_normals", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic("k_ingest_normals", nb), "peak_source": peak_src, "ms_per_launch": k1, "frames_per_launch": nb,
+                         "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
+                         "peak_source": peak_src, "ms_per_launch": k1, "frames_per_launch": nb,
                          "algorithmic_bytes_per_launch": K1K2_BYTES_PER_POINT * N * nb},
             "roofline_voxel_key": roof_voxel,
-            "kernels_of_a_chunk": {"frames": nb, "ms": round(chunk_ms, 4), "top": kernels,
-                                   "note": "k_cl_union (radius-graph union-find) and k_ransac are issue / latency bound on a few MB per chunk: no HBM roofline applies; "
-                                           "k_ingest_normals is the largest kernel that streams the whole input"},
-            "stage_ms_last_chunk": stage_full, "voxel_stage_ms": float(np.mean(vox_ms)),
+            "roofline_voxel_stage": roof_vstage,
+            "kernels_of_a_chunk": {"frames": nb, "ms": round(chunk_ms, 4), "top": kernels},
+            "stage_ms_last_chunk": stage_full, "voxel_stage_ms": vstage_ms,
             "cpu_baseline": cpu,
         }
+        line.update(extras)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

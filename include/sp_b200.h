@@ -133,6 +133,21 @@ int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nfr
 int sp_process_frames_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int show_mode,
                              sp_frame_result *results);
 
+/* Compact records -- what a multi-GPU run exchanges and what a consumer of many frames reads: per frame the 16 leading
+ * int32 counters of sp_frame_result (64 bytes) followed by its n_planes sp_plane_record, frames back to back (about 3 KB per
+ * frame instead of 14 400 B).  Same processing as sp_process_frames(_device); the records never pass through host memory:
+ *   input_on_device : 0 = xyzrgba / R9 are host pointers, 1 = device pointers (same ordering precondition as above)
+ *   d_out           : DEVICE buffer of cap_bytes (sp_compact_bytes_max(nframes) always suffices)
+ *   d_offsets       : DEVICE array of nframes + 1 int64 byte offsets of the frames inside d_out, or NULL
+ *   total_bytes     : host, bytes written (also set when the call fails with SP_ERR_CAPACITY)
+ * sp_expand_compact (host only, no device work) turns a compact buffer back into fixed-size records.
+ * Replaces, for a batch, what DProcessor keeps of a frame: `vector_plane_sorted` without the clouds
+ * (/root/reference/test/processor.cpp:173-196). */
+int sp_process_frames_compact(sp_ctx *ctx, const void *xyzrgba, const float *R9, int input_on_device, int nframes, int show_mode,
+                              void *d_out, int64_t cap_bytes, int64_t *d_offsets, int64_t *total_bytes);
+int64_t sp_compact_bytes_max(int nframes);
+int sp_expand_compact(const void *compact, int64_t bytes, int nframes, sp_frame_result *out);
+
 /* Depth-image ingest -- the step BEFORE the path, so that 2-8 bytes per pixel cross PCIe instead of 16:
  * replaces K2G::updateCloud (/root/reference/modules/k2g/k2g.cpp:231-308, pinhole maps of K2G::prepareMake3D :506-520)
  * followed by everything sp_process_frames does.

@@ -46,11 +46,45 @@ TAP_DTYPES = {
 _lib = None
 
 
+def _host_signature():
+    """the oracle is built -march=native: a library built on another CPU model (it travels with the repo snapshot to the GPU
+    box) must be rebuilt there.  Signature = the CPU feature flags of this host."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    return hashlib.sha256(flags.encode()).hexdigest()[:16]
+
+
+def build_flags():
+    """the CXXFLAGS line of oracle/Makefile (recorded next to every CPU-baseline number)"""
+    with open(os.path.join(_HERE, "Makefile")) as f:
+        for line in f:
+            if line.startswith("CXXFLAGS"):
+                return "g++ " + line.split("=", 1)[1].strip()
+    return "unknown"
+
+
 def build(force=False):
     so = os.path.join(_HERE, "liborc.so")
-    srcs = [os.path.join(_HERE, f) for f in ("sp_oracle.cpp", "sp_oracle.h")] + [os.path.join(_HERE, "..", "include", "sp_detmath.h")]
-    if force or not os.path.exists(so) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    sig_file = so + ".host"
+    srcs = [os.path.join(_HERE, f) for f in ("sp_oracle.cpp", "sp_oracle.h", "indep_math.h", "Makefile")] + [os.path.join(_HERE, "..", "include", "sp_detmath.h")]
+    sig = _host_signature()
+    try:
+        with open(sig_file) as f:
+            same_host = f.read().strip() == sig
+    except OSError:
+        same_host = False
+    if force or not same_host or not os.path.exists(so) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        with open(sig_file, "w") as f:
+            f.write(sig + "\n")
     return so
 
 
@@ -72,6 +106,7 @@ def lib():
         L.orc_tap_names.restype = C.c_int64
         L.orc_tap_names.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.orc_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        L.orc_audit.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         L.orc_stage_name.restype = C.c_char_p
         L.orc_stage_name.argtypes = [C.c_int]
         L.orc_rotation_from_euler.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
@@ -153,6 +188,16 @@ class Oracle:
 
     def counts(self):
         return dict(zip(COUNT_NAMES, self.tap("counts").tolist()))
+
+    AUDIT_NAMES = ["n_eigen33", "n_jacobi", "n_acos", "n_log", "eigen33_max_angle", "eigen33_max_angle_wellsep", "eigen33_max_val",
+                   "jacobi_max_val", "jacobi_max_angle", "acos_max_abs", "log_max_rel"]
+
+    def audit(self):
+        """deviation of the shared-header numerics (include/sp_detmath.h) from the oracle's own (oracle/indep_math.h) over the
+        last frame processed with keep_taps"""
+        arr = (C.c_double * 16)()
+        n = self.L.orc_audit(self.h, arr, 16)
+        return {self.AUDIT_NAMES[i]: arr[i] for i in range(n)}
 
     def stage_ms(self):
         arr = (C.c_double * 16)()

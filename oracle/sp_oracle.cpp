@@ -15,6 +15,7 @@
  */
 #include "sp_oracle.h"
 #include "../include/sp_detmath.h"
+#include "indep_math.h"
 
 #include <algorithm>
 #include <chrono>
@@ -49,7 +50,10 @@ struct orc_ctx {
     orc_params p;
     int normal_arith = 1;    /* 0 = PCL integral images (double), 1 = fixed-order double box sums */
     int voxel_order = 0;     /* 0 = stable, 1 = std::sort on the key only */
-    int eig_math = 0;        /* 0 = portable det_* math, 1 = libm */
+    int eig_math = 0;        /* 0 = portable det_* math (shared with the product), 1 = the same restatement on libm trig,
+                                2 = the oracle's own numerics (oracle/indep_math.h: double Jacobi, libm acos / log) */
+    bool audit_on = false;   /* set by orc_process(keep_taps = 1): the timed baseline does not pay for the audit */
+    indep::Audit audit;      /* every eigen-solve, acos and log of the last frame re-done independently: largest deviations */
     int knn_threads = 8;     /* host threads of the kNN normal search (a3') */
     int acos_float = 0;      /* a8: 0 = acos((double)nx), 1 = (double)acosf(nx)  (overload ambiguity) */
     std::map<std::string, Tap> taps;
@@ -74,6 +78,83 @@ template <class T> void put_tap(orc_ctx *c, const char *name, const T *data, siz
 template <class T> void put_tap(orc_ctx *c, const char *name, const std::vector<T> &v) { put_tap(c, name, v.data(), v.size()); }
 
 inline bool finite3(float a, float b, float c) { return std::isfinite(a) && std::isfinite(b) && std::isfinite(c); }
+
+/* ---- the places where sp_detmath.h decides a result, each with its independent twin ------------------------------------ */
+inline void cov_upper(const float *cov9, double up[6]) { up[0] = cov9[0]; up[1] = cov9[1]; up[2] = cov9[2]; up[3] = cov9[4]; up[4] = cov9[5]; up[5] = cov9[8]; }
+
+/* smallest eigenpair of the refit / kNN covariance (pcl::eigen33).  mode 2 solves it with indep::sym3_eigen; the sign of an
+ * eigenvector is free, mode 2 makes its largest component positive.  audit (may be NULL) gets the deviation of modes 0 / 1. */
+void smallest_eigenpair(int mode, const float *cov9, float *ev, float *evec, indep::Audit *audit)
+{
+    double up[6], lam[3], vec[3][3];
+    if (mode == 2 || audit) { cov_upper(cov9, up); indep::sym3_eigen(up, lam, vec); }
+    if (mode == 2) {
+        int big = 0;
+        for (int k = 1; k < 3; ++k) if (std::fabs(vec[0][k]) > std::fabs(vec[0][big])) big = k;
+        const double sg = vec[0][big] < 0 ? -1.0 : 1.0;
+        *ev = (float)lam[0];
+        for (int k = 0; k < 3; ++k) evec[k] = (float)(sg * vec[0][k]);
+        return;
+    }
+    if (mode == 1) det_eigen33f<1>(cov9, ev, evec); else det_eigen33f<0>(cov9, ev, evec);
+    if (audit && std::isfinite(evec[0]) && lam[2] > 0.0) {
+        const double got[3] = { evec[0], evec[1], evec[2] };
+        const double ang = indep::axis_angle(got, vec[0]);
+        audit->n_eigen33++;
+        audit->eigen33_max_angle = std::max(audit->eigen33_max_angle, ang);
+        if (lam[1] - lam[0] > 0.05 * lam[2]) audit->eigen33_max_angle_wellsep = std::max(audit->eigen33_max_angle_wellsep, ang);
+        audit->eigen33_max_val = std::max(audit->eigen33_max_val, std::fabs((double)*ev - lam[0]) / lam[2]);
+    }
+}
+
+/* full decomposition of the plane covariance (Eigen::JacobiSVD of a symmetric PSD matrix): descending, vectors as columns */
+void full_eigen(int mode, const float *cov9, float *evals, float *evecs, indep::Audit *audit)
+{
+    double up[6], lam[3], vec[3][3];
+    if (mode == 2 || audit) { cov_upper(cov9, up); indep::sym3_eigen(up, lam, vec); }
+    if (mode == 2) {
+        for (int j = 0; j < 3; ++j) {
+            const int k = 2 - j;
+            int big = 0;
+            for (int r = 1; r < 3; ++r) if (std::fabs(vec[k][r]) > std::fabs(vec[k][big])) big = r;
+            const double sg = vec[k][big] < 0 ? -1.0 : 1.0;
+            evals[j] = (float)lam[k];
+            for (int r = 0; r < 3; ++r) evecs[r * 3 + j] = (float)(sg * vec[k][r]);
+        }
+        return;
+    }
+    det_jacobi3f(cov9, evals, evecs);
+    if (audit && lam[2] > 0.0) {
+        audit->n_jacobi++;
+        for (int j = 0; j < 3; ++j) {
+            const int k = 2 - j;
+            audit->jacobi_max_val = std::max(audit->jacobi_max_val, std::fabs((double)evals[j] - lam[k]) / lam[2]);
+            const double gap = std::min(k > 0 ? lam[k] - lam[k - 1] : 1e300, k < 2 ? lam[k + 1] - lam[k] : 1e300);
+            if (gap > 1e-3 * lam[2]) {
+                const double got[3] = { evecs[0 * 3 + j], evecs[1 * 3 + j], evecs[2 * 3 + j] };
+                audit->jacobi_max_angle = std::max(audit->jacobi_max_angle, indep::axis_angle(got, vec[k]));
+            }
+        }
+    }
+}
+
+inline float merge_acos(int mode, float dot, indep::Audit *audit)
+{
+    const float ref = (float)acos((double)dot);
+    if (mode != 0) return ref;
+    const float a = det_acosf(dot);
+    if (audit && std::isfinite(ref)) { audit->n_acos++; audit->acos_max_abs = std::max(audit->acos_max_abs, (double)std::fabs(a - ref)); }
+    return a;
+}
+
+inline double ransac_log(int mode, double x, indep::Audit *audit)
+{
+    const double ref = log(x);
+    if (mode != 0) return ref;
+    const double v = det_log(x);
+    if (audit && ref != 0.0) { audit->n_log++; audit->log_max_rel = std::max(audit->log_max_rel, std::fabs((v - ref) / ref)); }
+    return v;
+}
 
 /* pcl::deg2rad(float), upstream common/impl/angles.hpp */
 inline float deg2radf(float a) { return a * 0.017453293f; }
@@ -314,7 +395,7 @@ void normals_knn(orc_ctx *c, int k, int nthreads)
             cov[4] = accu[3] - accu[7] * accu[7]; cov[5] = accu[4] - accu[7] * accu[8]; cov[8] = accu[5] - accu[8] * accu[8];
             cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
             float ev, evec[3];
-            if (c->eig_math) det_eigen33f<1>(cov, &ev, evec); else det_eigen33f<0>(cov, &ev, evec);
+            smallest_eigenpair(c->eig_math, cov, &ev, evec, nullptr);      /* (the audit of eigen33 runs on the refits: single-threaded) */
             float fx = evec[0], fy = evec[1], fz = evec[2];
             const float vx = 0.0f - X[i], vy = 0.0f - Y[i], vz = 0.0f - Z[i];
             const float cs = (vx * fx + vy * fy + vz * fz);
@@ -469,7 +550,7 @@ void euclidean_clusters(orc_ctx *c, const std::vector<int> &pix, std::vector<std
 struct Pts { std::vector<float> x, y, z; std::vector<int> pix; int n() const { return (int)x.size(); } };
 
 struct SegCfg {
-    int max_iters; float thr; bool parallel; double sin_angle; int eig_math;
+    int max_iters; float thr; bool parallel; double sin_angle; int eig_math; indep::Audit *audit;
 };
 
 /* Eigen packet reduction of a 4-float dot: (a0+a1)+(a2+a3) */
@@ -539,7 +620,7 @@ bool segment_once(const SegCfg &cfg, const Pts &P, std::vector<int> &inliers, fl
     for (int i = 0; i < n; ++i) sh[i] = i;
     int iterations = 0, best = -std::numeric_limits<int>::max();
     double k = 1.0;
-    const double log_probability = cfg.eig_math ? log(1.0 - 0.99) : det_log(1.0 - 0.99);
+    const double log_probability = ransac_log(cfg.eig_math, 1.0 - 0.99, cfg.audit);
     const double one_over = 1.0 / (double)n;
     unsigned skipped = 0; const unsigned max_skip = (unsigned)cfg.max_iters * 10u;
     float best_m[4] = { 0, 0, 0, 0 }; bool have = false;
@@ -563,7 +644,7 @@ bool segment_once(const SegCfg &cfg, const Pts &P, std::vector<int> &inliers, fl
             double p_no = 1.0 - (cfg.eig_math ? pow(w, 3.0) : w * w * w);
             p_no = std::max(std::numeric_limits<double>::epsilon(), p_no);
             p_no = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no);
-            k = log_probability / (cfg.eig_math ? log(p_no) : det_log(p_no));
+            k = log_probability / ransac_log(cfg.eig_math, p_no, cfg.audit);
         }
         ++iterations;
         if (iterations > cfg.max_iters) break;
@@ -588,7 +669,7 @@ bool segment_once(const SegCfg &cfg, const Pts &P, std::vector<int> &inliers, fl
         cov[4] = accu[3] - accu[7] * accu[7]; cov[5] = accu[4] - accu[7] * accu[8]; cov[8] = accu[5] - accu[8] * accu[8];
         cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
         float ev, evec[3];
-        if (cfg.eig_math) det_eigen33f<1>(cov, &ev, evec); else det_eigen33f<0>(cov, &ev, evec);
+        smallest_eigenpair(cfg.eig_math, cov, &ev, evec, cfg.audit);
         refined[0] = evec[0]; refined[1] = evec[1]; refined[2] = evec[2];
         refined[3] = -1 * dot4(evec[0], evec[1], evec[2], 0.0f, accu[6], accu[7], accu[8], 1.0f);
         if (!model_valid(cfg, refined)) memcpy(refined, best_m, sizeof(refined));
@@ -609,7 +690,7 @@ void segment_planes(orc_ctx *c, const std::vector<int> &pix, bool vertical, std:
     SegCfg cfg;
     cfg.max_iters = c->p.seg_max_iters; cfg.thr = (float)c->p.seg_threshold; cfg.parallel = vertical;
     const float eps = deg2radf((float)c->p.seg_plane_angle_diff);
-    cfg.sin_angle = fabs(sin((double)eps)); cfg.eig_math = c->eig_math;
+    cfg.sin_angle = fabs(sin((double)eps)); cfg.eig_math = c->eig_math; cfg.audit = c->audit_on ? &c->audit : nullptr;
     const int rest = c->p.seg_rest_point;
     for (size_t ci = 0; ci < clusters.size(); ++ci) {
         Pts P;
@@ -687,7 +768,7 @@ void merge_planes(orc_ctx *c, std::vector<SegPlane> &planes)
         for (size_t j = i + 1; j < planes.size(); ++j) {
             const float a2 = planes[j].coef[0], b2 = planes[j].coef[1], c2 = planes[j].coef[2], d2 = planes[j].coef[3];
             const float dot = a1 * a2 + (b1 * b2 + c1 * c2);                   /* Eigen Vector3f dot: v0 + (v1 + v2) */
-            const float angle = c->eig_math ? (float)acos((double)dot) : det_acosf(dot);
+            const float angle = merge_acos(c->eig_math, dot, c->audit_on ? &c->audit : nullptr);
             if (((double)angle < ath) || (M_PI - (double)angle < ath)) {
                 size_t count = 0;
                 for (int k = 0; k < S; ++k) {
@@ -736,7 +817,7 @@ void plane_info(orc_ctx *c, const SegPlane &sp, int type, orc_plane_record &r)
     }
     float cov[9] = { s[0] / fn, s[1] / fn, s[2] / fn, s[1] / fn, s[3] / fn, s[4] / fn, s[2] / fn, s[4] / fn, s[5] / fn };
     float evals[3], evecs[9];
-    det_jacobi3f(cov, evals, evecs);
+    full_eigen(c->eig_math, cov, evals, evecs, c->audit_on ? &c->audit : nullptr);
     for (int j = 0; j < 3; ++j) { r.eval[j] = evals[j]; for (int k = 0; k < 3; ++k) r.evec[3 * j + k] = evecs[k * 3 + j]; }
     float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
     int imn[3] = { -1, -1, -1 }, imx[3] = { -1, -1, -1 };
@@ -793,6 +874,7 @@ int orc_process(orc_ctx *c, const void *xyzrgba, int width, int height, const fl
     if (!c || !xyzrgba || width <= 0 || height <= 0) return -1;
     c->taps.clear(); c->records.clear(); c->plane_idx.clear(); c->rand_pos = 0;
     memset(c->stage_ms, 0, sizeof(c->stage_ms));
+    c->audit.reset(); c->audit_on = keep_taps != 0;
     c->W = width; c->H = height; c->N = width * height;
     int32_t counts[16]; memset(counts, 0, sizeof(counts));   /* same order as sp_frame_result's leading ints */
     auto finish = [&](int status) { counts[0] = status; put_tap(c, "counts", counts, 16); return (int)c->records.size(); };
@@ -948,6 +1030,16 @@ int64_t orc_tap_names(orc_ctx *c, char *dst, int64_t cap)
     return (int64_t)s.size() + 1;
 }
 
+/* the audit of the last orc_process(keep_taps = 1) call, see oracle/indep_math.h: 11 doubles */
+int orc_audit(orc_ctx *c, double *out, int cap)
+{
+    const indep::Audit &a = c->audit;
+    const double v[11] = { (double)a.n_eigen33, (double)a.n_jacobi, (double)a.n_acos, (double)a.n_log, a.eigen33_max_angle, a.eigen33_max_angle_wellsep,
+                           a.eigen33_max_val, a.jacobi_max_val, a.jacobi_max_angle, a.acos_max_abs, a.log_max_rel };
+    const int n = std::min(cap, 11);
+    for (int i = 0; i < n; ++i) out[i] = v[i];
+    return n;
+}
 int orc_stage_ms(orc_ctx *c, double *out, int cap) { int n = std::min(cap, (int)ST_COUNT); for (int i = 0; i < n; ++i) out[i] = c->stage_ms[i]; return n; }
 const char *orc_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 

@@ -69,7 +69,9 @@ void orc_destroy(orc_ctx *c);
  *                       (the portable definition the CUDA kernel reproduces bit for bit).  Default 1.
  *   "voxel_order":  0 = stable (ascending input index inside a voxel; the documented rule), default;
  *                   1 = libstdc++ std::sort on the key only (what the reference binary would do with g++).
- *   "eig_math":     0 = portable det_* trig from include/sp_detmath.h (default), 1 = libm.
+ *   "eig_math":     0 = portable det_* math from include/sp_detmath.h, the header the product compiles too (default);
+ *                   1 = the same restatements on libm trig; 2 = the oracle's own numerics (oracle/indep_math.h: double
+ *                   Jacobi eigen-solver, libm acos / log) -- shares nothing with the product.
  * returns 0, or -1 for an unknown name. */
 int orc_set_mode(orc_ctx *c, const char *name, int value);
 
@@ -92,6 +94,12 @@ int64_t orc_tap_bytes(orc_ctx *c, const char *name);          /* -1 if absent */
 int64_t orc_tap_copy(orc_ctx *c, const char *name, void *dst, int64_t cap);
 /* names of all taps, '\n'-separated, into dst; returns bytes needed */
 int64_t orc_tap_names(orc_ctx *c, char *dst, int64_t cap);
+
+/* Audit of the last orc_process(keep_taps = 1) call in eig_math 0 / 1: every eigen-solve, acos and log re-done with the
+ * oracle's own numerics (oracle/indep_math.h).  out = { n_eigen33, n_jacobi, n_acos, n_log, eigen33 max angle [rad],
+ * the same over well-separated spectra, eigen33 max |lambda0 - ref| / lambda_max, jacobi max |eval - ref| / lambda_max,
+ * jacobi max eigenvector angle, acos max abs error, log max relative error }.  Returns the number written. */
+int orc_audit(orc_ctx *c, double *out, int cap);
 
 /* per-stage wall time of the last orc_process call, milliseconds; returns number written */
 int orc_stage_ms(orc_ctx *c, double *out, int cap);

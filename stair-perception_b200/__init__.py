@@ -72,6 +72,11 @@ def lib():
         L.sp_set_normal_mode.argtypes = [C.c_void_p, C.c_int]
         L.sp_set_trace.argtypes = [C.c_void_p, C.c_int]
         L.sp_trace_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+        L.sp_process_frames_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                                C.POINTER(C.c_int64)]
+        L.sp_compact_bytes_max.restype = C.c_int64
+        L.sp_compact_bytes_max.argtypes = [C.c_int]
+        L.sp_expand_compact.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         L.sp_stream.restype = C.c_void_p
         L.sp_stream.argtypes = [C.c_void_p]
         _lib = L
@@ -202,6 +207,26 @@ class Context:
             torch.cuda.current_stream(clouds.device).synchronize()
         self._check(fn(self.h, _ptr(clouds), Rp, nframes, int(show_mode), results.ctypes.data), "sp_process_frames")
         return results
+
+    def process_frames_compact(self, clouds, R=None, show_mode=10, nframes=None, device_input=False, out=None, offsets=None):
+        """Same processing, compact records left ON THE DEVICE: `out` is a torch uint8 CUDA tensor (made here when None; any
+        capacity >= compact_bytes_max(nframes) always suffices), `offsets` an optional int64 CUDA tensor of nframes + 1 entries.
+        Returns (out, nbytes): out[:nbytes] holds {16 int32 counters, n_planes plane records} per frame, back to back."""
+        import torch
+        nbytes = clouds.nbytes if isinstance(clouds, np.ndarray) else clouds.numel() * clouds.element_size()
+        if nframes is None:
+            nframes = nbytes // (self.N * 16)
+        if nbytes < nframes * self.N * 16:
+            raise ValueError("cloud buffer too small")
+        if out is None:
+            out = torch.empty(int(self.L.sp_compact_bytes_max(nframes)), dtype=torch.uint8, device="cuda")
+        if device_input and hasattr(clouds, "is_cuda") and clouds.is_cuda:
+            torch.cuda.current_stream(clouds.device).synchronize()
+        total = C.c_int64(0)
+        self._check(self.L.sp_process_frames_compact(self.h, _ptr(clouds), None if R is None else _ptr(R), 1 if device_input else 0, nframes,
+                                                     int(show_mode), out.data_ptr(), out.numel(), None if offsets is None else offsets.data_ptr(),
+                                                     C.byref(total)), "sp_process_frames_compact")
+        return out, int(total.value)
 
     def process_depth_frames(self, depth, intrinsics, bgrx=None, mirror=True, R=None, show_mode=10, nframes=None, results=None):
         """depth: float32 or uint16 millimetres, nframes x H x W (numpy or pinned torch CPU tensor); intrinsics = (fx, fy, cx, cy);
@@ -334,6 +359,25 @@ class StairDetection:
             self.last_stair = ctx.stair_model(0)
             return bool(self.last_stair["has_stair"]), planes, res
         return False, planes, res
+
+
+def expand_compact(buf, nframes):
+    """host-side: compact records (numpy uint8 / bytes) -> FRAME_DTYPE array of nframes fixed-size records"""
+    b = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.view(np.uint8).reshape(-1))
+    out = np.zeros(nframes, dtype=FRAME_DTYPE)
+    rc = lib().sp_expand_compact(b.ctypes.data, b.nbytes, nframes, out.ctypes.data)
+    if rc != 0:
+        raise SpError("sp_expand_compact: malformed compact buffer (%d)" % rc)
+    return out
+
+
+def compact_records(results):
+    """host-side inverse of expand_compact (numpy): FRAME_DTYPE records -> compact bytes"""
+    parts = []
+    for r in results:
+        raw = np.frombuffer(r.tobytes(), dtype=np.uint8)
+        parts.append(raw[:64 + int(r["n_planes"]) * PLANE_DTYPE.itemsize])
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
 
 
 def stair_steps(stair):

@@ -13,12 +13,16 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <random>
 #include <string>
 #include <vector>
+
+static_assert(offsetof(sp_frame_result, planes) == SP_COMPACT_HEADER && sizeof(sp_frame_result) == SP_COMPACT_HEADER + SP_MAX_PLANES * sizeof(sp_plane_record),
+              "compact records = the 16 leading counters + n_planes plane records");
 
 namespace {
 
@@ -129,6 +133,10 @@ struct sp_ctx {
     std::vector<const char *> tname;
     int tn = 0;
     int last_nB = 0;
+    sp_frame_result *last_res = nullptr;      /* device records of the last chunk: the lane's own array, or a slice of the batch array */
+    sp_frame_result *d_batch_res = nullptr;   /* records of a whole batch on the device (compact entry point), grown on demand */
+    size_t batch_res_cap = 0;
+    long long *d_coff = nullptr; size_t coff_cap = 0;
     int64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -171,10 +179,12 @@ void mark(sp_ctx *ctx, const char *name)
 }
 
 /* the per-chunk launch sequence; only_stage: -1 = everything `show_mode` asks for, 0 / 1 = one stage group, 2 = all */
-int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int show_mode, int only_stage)
+int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int show_mode, int only_stage, sp_frame_result *res = nullptr)
 {
     SpDev d = ctx->d;
     d.in = d_in; d.R = d_R; d.B = nB;
+    if (res) d.results = res;                                 /* records go straight into the batch array */
+    ctx->last_res = d.results;
     cudaStream_t st = ctx->stream;
     const int N = ctx->N;
     ctx->last_nB = nB;
@@ -439,6 +449,8 @@ void sp_destroy(sp_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->d_batch_res) cudaFree(ctx->d_batch_res);
+    if (ctx->d_coff) cudaFree(ctx->d_coff);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     for (int i = 0; i <= STG_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
@@ -536,13 +548,21 @@ static int lanes_for(sp_ctx *ctx, int nchunks, sp_ctx **lanes)
     return nl;
 }
 
-static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results, bool host_in)
+/* results != NULL: fixed-size records to host memory, chunk by chunk behind the kernels.  results == NULL (compact entry
+ * point): the records of the whole batch stay on the device in ctx->d_batch_res. */
+static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results, bool host_in, bool keep_on_device = false)
 {
-    if (!ctx || !xyzrgba || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR || (!results && nframes > 0)) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx || !xyzrgba || nframes < 0 || show_mode < 0 || show_mode > SP_SHOW_STAIR || (!results && !keep_on_device && nframes > 0)) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     const size_t fb = (size_t)ctx->N * 16;
-    if (show_mode == SP_SHOW_ORIGINAL) { memset(results, 0, sizeof(sp_frame_result) * (size_t)nframes); return SP_OK; }
+    if (keep_on_device) {
+        if ((size_t)nframes > ctx->batch_res_cap) {
+            if (ctx->d_batch_res) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_batch_res); ctx->d_batch_res = nullptr; ctx->batch_res_cap = 0; }
+            CK(cudaMalloc((void **)&ctx->d_batch_res, sizeof(sp_frame_result) * (size_t)nframes));
+            ctx->batch_res_cap = (size_t)nframes;
+        }
+        if (show_mode == SP_SHOW_ORIGINAL) { CK(cudaMemsetAsync(ctx->d_batch_res, 0, sizeof(sp_frame_result) * (size_t)nframes, ctx->stream)); return SP_OK; }
+    } else if (show_mode == SP_SHOW_ORIGINAL) { memset(results, 0, sizeof(sp_frame_result) * (size_t)nframes); return SP_OK; }
     int buf = 0;
     /* chunk loop; with host input the H2D copy of chunk i+1 (copy stream) overlaps the kernels of chunk i; with two or more
      * chunks the chunks alternate between two lanes (this context and its twin), each with its own workspace and stream */
@@ -595,14 +615,17 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         } else {
             din = (const float4 *)((const uint8_t *)xyzrgba + fb * f0); dR = R9 ? R9 + 9 * (size_t)f0 : nullptr;
         }
-        CK(cudaMemsetAsync(L->d.results, 0, sizeof(sp_frame_result) * nB, L->stream));
-        const int rc = run_chunk(L, din, dR, nB, show_mode, -1);
+        sp_frame_result *dres = keep_on_device ? ctx->d_batch_res + f0 : L->d.results;
+        CK(cudaMemsetAsync(dres, 0, sizeof(sp_frame_result) * nB, L->stream));
+        const int rc = run_chunk(L, din, dR, nB, show_mode, -1, keep_on_device ? dres : nullptr);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_done[buf], L->stream));
-        CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
-        CK(cudaEventRecord(L->ev_res[hb], L->stream));
-        pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
-        { const int rd = drain((size_t)nl); if (rd) return rd; }
+        if (!keep_on_device) {
+            CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
+            CK(cudaEventRecord(L->ev_res[hb], L->stream));
+            pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
+            { const int rd = drain((size_t)nl); if (rd) return rd; }
+        }
         buf ^= 1;
     }
     { const int rd = drain(0); if (rd) return rd; }
@@ -714,12 +737,60 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
 
 int sp_process_frames(sp_ctx *ctx, const void *xyzrgba, const float *R9, int nframes, int show_mode, sp_frame_result *results)
 {
+    if (!ctx) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     return process_impl(ctx, xyzrgba, R9, nframes, show_mode, results, true);
 }
 
 int sp_process_frames_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int show_mode, sp_frame_result *results)
 {
+    if (!ctx) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     return process_impl(ctx, d_xyzrgba, d_R9, nframes, show_mode, results, false);
+}
+
+int sp_process_frames_compact(sp_ctx *ctx, const void *xyzrgba, const float *R9, int input_on_device, int nframes, int show_mode,
+                              void *d_out, int64_t cap_bytes, int64_t *d_offsets, int64_t *total_bytes)
+{
+    if (!ctx || !xyzrgba || nframes < 0 || (!d_out && cap_bytes > 0) || cap_bytes < 0) { if (ctx) ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int rc = process_impl(ctx, xyzrgba, R9, nframes, show_mode, nullptr, input_on_device == 0, true);
+    if (rc != SP_OK) return rc;
+    if ((size_t)nframes + 1 > ctx->coff_cap) {
+        if (ctx->d_coff) cudaFree(ctx->d_coff);
+        ctx->d_coff = nullptr; ctx->coff_cap = 0;
+        CK(cudaMalloc((void **)&ctx->d_coff, sizeof(long long) * ((size_t)nframes + 1)));
+        ctx->coff_cap = (size_t)nframes + 1;
+    }
+    /* every lane has been synchronised by process_impl: the records are complete */
+    k_compact_offsets<<<1, 1024, 0, ctx->stream>>>(ctx->d_batch_res, nframes, ctx->d_coff);
+    if (nframes > 0) k_compact_copy<<<nframes, 128, 0, ctx->stream>>>(ctx->d_batch_res, nframes, ctx->d_coff, (unsigned char *)d_out, (long long)cap_bytes);
+    ctx->launches += 2;
+    if (d_offsets) CK(cudaMemcpyAsync(d_offsets, ctx->d_coff, sizeof(long long) * ((size_t)nframes + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    long long total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->d_coff + nframes, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (total_bytes) *total_bytes = (int64_t)total;
+    if (total > (long long)cap_bytes) { ERR(ctx) = "compact buffer too small"; return SP_ERR_CAPACITY; }
+    return SP_OK;
+}
+
+int64_t sp_compact_bytes_max(int nframes) { return (int64_t)nframes * (int64_t)sizeof(sp_frame_result); }
+
+int sp_expand_compact(const void *compact, int64_t bytes, int nframes, sp_frame_result *out)
+{
+    if ((!compact && bytes > 0) || !out || nframes < 0 || bytes < 0) return SP_ERR_ARG;
+    const uint8_t *p = (const uint8_t *)compact, *end = p + bytes;
+    for (int f = 0; f < nframes; ++f) {
+        if (end - p < SP_COMPACT_HEADER) return SP_ERR_ARG;
+        memset(&out[f], 0, sizeof(sp_frame_result));
+        memcpy(&out[f], p, SP_COMPACT_HEADER);
+        const int np = out[f].n_planes;
+        if (np < 0 || np > SP_MAX_PLANES || end - (p + SP_COMPACT_HEADER) < (int64_t)np * (int64_t)sizeof(sp_plane_record)) return SP_ERR_ARG;
+        memcpy(out[f].planes, p + SP_COMPACT_HEADER, (size_t)np * sizeof(sp_plane_record));
+        p += SP_COMPACT_HEADER + (size_t)np * sizeof(sp_plane_record);
+    }
+    return p == end ? SP_OK : SP_ERR_ARG;
 }
 
 int sp_run_stage_device(sp_ctx *ctx, const void *d_xyzrgba, const float *d_R9, int nframes, int stage)
@@ -882,7 +953,7 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         }
     }
     if (name == "plane_idx") {
-        sp_frame_result r; CK(d2h(&r, d.results + f, sizeof(r)));
+        sp_frame_result r; CK(d2h(&r, ctx->last_res + f, sizeof(r)));
         std::vector<int> v(r.n_plane_points); CK(d2h(v.data(), d.plane_idx + f * N, (size_t)r.n_plane_points * 4));
         put_i(v); return SP_OK;
     }
@@ -921,7 +992,7 @@ int sp_copy_plane_points(sp_ctx *ctx, int frame, int plane, float *xyz, int32_t 
     CK(cudaStreamSynchronize(ctx->stream));
     const SpDev &d = ctx->d;
     const size_t N = ctx->N, f = frame;
-    sp_frame_result r; CK(cudaMemcpy(&r, d.results + f, sizeof(r), cudaMemcpyDeviceToHost));
+    sp_frame_result r; CK(cudaMemcpy(&r, ctx->last_res + f, sizeof(r), cudaMemcpyDeviceToHost));
     if (plane >= r.n_planes) { ERR(ctx) = "plane out of range"; return SP_ERR_ARG; }
     const int n = std::min(cap, r.planes[plane].count);
     std::vector<int> idx(n);
@@ -984,7 +1055,7 @@ int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out)
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<sp_frame_result> fr(1);
-    CK(cudaMemcpy(fr.data(), ctx->d.results + frame, sizeof(sp_frame_result), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fr.data(), ctx->last_res + frame, sizeof(sp_frame_result), cudaMemcpyDeviceToHost));
     DevicePoints pts; pts.ctx = ctx; pts.frame = frame; pts.fr = fr.data();
     sp_stairmodel::stair_model(ctx->params, fr[0], pts, out);
     return SP_OK;
@@ -1030,7 +1101,7 @@ int sp_minmax_proj(sp_ctx *ctx, int frame, int plane, const float *center3, cons
     const SpDev &d = ctx->d;
     const size_t N = ctx->N, f = frame;
     sp_frame_result *r = new sp_frame_result;
-    cudaError_t e = cudaMemcpy(r, d.results + f, sizeof(*r), cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(r, ctx->last_res + f, sizeof(*r), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess || plane >= r->n_planes) { const bool bad = e == cudaSuccess; delete r; ERR(ctx) = bad ? "plane out of range" : cudaGetErrorString(e); return bad ? SP_ERR_ARG : SP_ERR_CUDA; }
     const sp_plane_record pr = r->planes[plane];
     delete r;

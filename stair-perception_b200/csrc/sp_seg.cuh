@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) k_merge(SpDev d, int nB)
                  * fewer points than there are planes (only possible when seg_rest_point < plane count) it reads out of bounds.
                  * Here: a NaN sample, which never counts as near, and a capacity flag on the frame. */
                 float4 pw = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), 0.f);
-                if (pi >= 0) pw = PT[pi]; else atomicOr(&d.flags[f], 8);
+                if (pi >= 0) pw = PT[pi]; else atomicOr(&d.flags[f], 16);
                 S.sx[i][lane] = pw.x; S.sy[i][lane] = pw.y; S.sz[i][lane] = pw.z;
             }
             rpos += 20;
@@ -1061,4 +1061,43 @@ __global__ void __launch_bounds__(256) k_minmax_proj(SpDev d, int frame, int fir
         }
         out[0] = amx; out[1] = amn;
     }
+}
+
+/* ==================================================================================================== */
+/* Compact records: what a multi-GPU run exchanges and what a consumer of many frames reads.  Frame f of a batch becomes
+ * { 16 int32 = the leading counters of sp_frame_result, n_planes x sp_plane_record }, frames back to back.
+ * k_compact_offsets: byte offset of every frame (one CTA, exclusive scan); k_compact_copy: one CTA per frame. */
+#define SP_COMPACT_HEADER 64
+__global__ void __launch_bounds__(1024) k_compact_offsets(const sp_frame_result *res, int nframes, long long *off)
+{
+    __shared__ long long ws[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int f0 = 0; f0 < nframes; f0 += 1024) {
+        const int f = f0 + threadIdx.x;
+        const long long v = f < nframes ? (long long)SP_COMPACT_HEADER + (long long)sizeof(sp_plane_record) * res[f].n_planes : 0;
+        long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) ws[wid] = inc;
+        __syncthreads();
+        long long add = carry;
+        for (int w = 0; w < wid; ++w) add += ws[w];
+        if (f < nframes) off[f] = add + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = add + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[nframes] = carry;
+}
+
+__global__ void __launch_bounds__(128) k_compact_copy(const sp_frame_result *res, int nframes, const long long *off, unsigned char *out, long long cap)
+{
+    const int f = blockIdx.x;
+    if (f >= nframes || off[f + 1] > cap) return;             /* a buffer too small is reported by the host from off[nframes] */
+    const int words = (int)((off[f + 1] - off[f]) / 4);
+    const int *src = reinterpret_cast<const int *>(res + f);
+    int *dst = reinterpret_cast<int *>(out + off[f]);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
 }

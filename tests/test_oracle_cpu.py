@@ -314,3 +314,31 @@ def test_stair_model_on_synthetic_ground_truth(sp, orc, synth):
         steps = np.array(res["steps"])
         assert np.abs(steps[:, 0] - 0.11).max() < 3e-3
         assert np.abs(steps[:-1, 1] - 0.28).max() < 3e-3
+
+
+def test_shared_numerics_audited_against_independent_ones(sp, orc, samples, synth):
+    """include/sp_detmath.h (eigen33, Jacobi, acos, log) is compiled into the product AND into the oracle's default mode, so the
+    bit-exact parity tests cannot see a wrong restatement in it.  Two independent checks (oracle/indep_math.h: classical double
+    Jacobi + libm, sharing nothing with that header):
+      - the audit re-solves every eigen problem / acos / log of a frame and bounds the deviation of the shared-header result;
+      - eig_math = 2 runs the whole pipeline on the independent numerics: same planes, coefficients within 1e-4 (the stated
+        tolerance for plane coefficients), centres identical."""
+    cases = [(samples["0000"][0], None), (samples["0001"][0], None)] + [synth.make_frame(f) for f in (2, 9)]
+    for rec, R in cases:
+        o = orc.Oracle(sp.DEFAULT_PARAMS)
+        o.process(rec, 512, 424, R)
+        a = o.audit()
+        assert a["n_eigen33"] >= 5 and a["n_jacobi"] >= 5 and a["n_log"] >= 10
+        assert a["eigen33_max_angle_wellsep"] < 1e-5 and a["eigen33_max_val"] < 1e-4
+        assert a["jacobi_max_val"] < 1e-5 and a["jacobi_max_angle"] < 1e-4
+        assert a["acos_max_abs"] < 1e-6 and a["log_max_rel"] < 1e-13
+        o2 = orc.Oracle(sp.DEFAULT_PARAMS, eig_math=2)
+        o2.process(rec, 512, 424, R)
+        p0, p2 = o.tap("planes"), o2.tap("planes")
+        assert len(p0) == len(p2) and len(p0) >= 6
+        for q0, q2 in zip(p0, p2):
+            sg = np.sign(np.dot(q0["coef"][:3], q2["coef"][:3]))
+            assert int(q0["count"]) == int(q2["count"])
+            assert np.abs(q0["coef"] - sg * q2["coef"]).max() < 1e-4
+            assert np.abs(q0["center"] - q2["center"]).max() < 1e-6
+            assert np.allclose(q0["eval"], q2["eval"], rtol=1e-3, atol=1e-9)

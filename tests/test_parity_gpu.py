@@ -445,3 +445,23 @@ def test_two_lane_chunk_pipeline_keeps_order_and_bits(sp, synth, monkeypatch):
     got_d = ctx.process_depth_frames(depth, synth.INTRINSICS, bgrx=bgrx, mirror=True, R=Rs[:7], nframes=7)
     assert got_d.tobytes() == want_d.tobytes()
     ctx.close()
+
+
+def test_product_against_the_oracles_independent_numerics(sp, orc, samples, synth, ctx1):
+    """the product and the oracle's default mode share include/sp_detmath.h; eig_math = 2 runs the oracle on its own numerics
+    (oracle/indep_math.h: double Jacobi, libm).  Tolerance test next to the bit-exact ones: same plane count and sizes,
+    coefficients within 1e-4 (sign of a normal is free), centres within 1e-6, eigenvalues within 1e-3 relative."""
+    cases = [(samples["0000"][0], None), (samples["0001"][0], None)] + [synth.make_frame(f) for f in (2, 9)]
+    for rec, R in cases:
+        res = ctx1.process_frames(rec, None if R is None else R.reshape(1, 9))[0]
+        o2 = orc.Oracle(sp.DEFAULT_PARAMS, eig_math=2)
+        o2.process(rec, 512, 424, R)
+        p2 = o2.tap("planes")
+        assert int(res["n_planes"]) == len(p2) and len(p2) >= 6
+        for i, q2 in enumerate(p2):
+            q = res["planes"][i]
+            sg = np.sign(np.dot(q["coef"][:3], q2["coef"][:3]))
+            assert int(q["count"]) == int(q2["count"]) and int(q["type"]) == int(q2["type"])
+            assert np.abs(q["coef"] - sg * q2["coef"]).max() < 1e-4
+            assert np.abs(q["center"] - q2["center"]).max() < 1e-6
+            assert np.allclose(q["eval"], q2["eval"], rtol=1e-3, atol=1e-9)

@@ -56,6 +56,15 @@ def _worker(rank, world, port, nframes, outdir):
                 local[i - lo]["planes"][j][fld] = pl[j][fld]
     full = shard.gather_results(local, nframes)
     np.save(os.path.join(outdir, "rank%d.npy" % rank), full.view(np.uint8))
+    # the compact exchange of the GPU path (sp_process_frames_compact + shard.gather_compact), here on CPU tensors over gloo:
+    # header + n_planes records per frame, a buffer sized like sp_compact_bytes_max, then expanded again
+    import torch
+    mine = sp.compact_records(local)
+    buf = torch.zeros(int(sp.lib().sp_compact_bytes_max(max(shard.shard_sizes(nframes, world)))), dtype=torch.uint8)
+    buf[:mine.size] = torch.from_numpy(mine)
+    packed, sizes = shard.gather_compact(buf, int(mine.size))
+    assert len(sizes) == world and sizes[rank] == mine.size and packed.size == sum(sizes)
+    np.save(os.path.join(outdir, "compact%d.npy" % rank), sp.expand_compact(packed, nframes).view(np.uint8))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,6 +75,8 @@ def test_two_rank_gather_equals_single_process(sp, orc, synth, tmp_path):
     mp.spawn(_worker, args=(world, port, nframes, str(tmp_path)), nprocs=world, join=True)
     got = [np.load(os.path.join(str(tmp_path), "rank%d.npy" % r)).view(sp.FRAME_DTYPE) for r in range(world)]
     assert np.array_equal(got[0].view(np.uint8), got[1].view(np.uint8)) and len(got[0]) == nframes
+    for r in range(world):                                    # the compact exchange reassembles the very same records
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), "compact%d.npy" % r)), got[0].view(np.uint8).reshape(-1))
     for i in range(nframes):
         rec, R = synth.make_frame(100 + i)
         o = orc.Oracle(sp.DEFAULT_PARAMS)
