@@ -48,16 +48,17 @@ struct __align__(128) StSmem {
     float4 P[ST_PR][ST_T];                /* levelled + masked points {x, y, z, 0} */
     float4 GA[ST_GR][ST_T];               /* gradients {dx.x, dx.y, dx.z, dy.x} */
     float2 GB[ST_GR][ST_T];               /*           {dy.y, dy.z} */
-    double2 CS[3][ST_T];                  /* 5-row column sums of the six gradient channels, centre row i - 6 */
-    /* bit rows, one word per warp (+ a zero guard word at either end): [row ring][warp + 1] */
-    unsigned hp[ST_WR][ST_NW + 2], vp[ST_WR][ST_NW + 2];      /* depth-change pair flags: (c, c + 1) and (r, r + 1) */
-    unsigned fa[ST_WR][ST_NW + 2], fb[ST_WR][ST_NW + 2];      /* finite dx / dy gradient elements */
-    unsigned rk[ST_WR][ST_NW + 2], vm[ST_WR][ST_NW + 2];      /* inexact-risk coordinates; pixels that may get a normal */
-    unsigned short slow[2][ST_T + 32];    /* per finished row: pixels that take the ordered sums (column | window << 12) */
-    int nslow[2];
+    double2 CS[2][3][ST_T];               /* 5-row column sums of the six gradient channels, centre row i - 6; double-buffered by step */
+    unsigned hist[2][ST_T];               /* per column: the vertical bit histories the window logic needs (see ST_H_*), by step parity */
+    unsigned hedge[2][ST_NW + 1];         /* horizontal pair flag of each warp's last lane (its right neighbour is the next warp's lane 0) */
     int anyrisk;
     unsigned long long mbar[ST_RAW];
 };
+/* hist word of a column after the step that ingested row i: bits 0..8 depth-change flags of rows i - 2 .. i - 10, bits 9..13 / 14..18
+ * finite dx / dy gradient elements of rows i - 4 .. i - 8, bits 19..28 inexact-risk coordinates of rows i .. i - 9 */
+#define ST_H_FA 9
+#define ST_H_FB 14
+#define ST_H_RK 19
 
 __device__ __forceinline__ unsigned st_sptr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -86,13 +87,6 @@ __device__ __forceinline__ void st_tma_row(const CUtensorMap *tmap, void *dst, u
 {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  ::"r"(st_sptr(dst)), "l"((unsigned long long)tmap), "r"(0), "r"(col), "r"(row), "r"(frame), "r"(st_sptr(bar)) : "memory");
-}
-
-/* 64-bit window of a bit row around warp `wid`: bit 16 + k = column k of the warp, 16 columns of margin either side */
-__device__ __forceinline__ unsigned long long st_local(const unsigned (*rows)[ST_NW + 2], int slot, int wid)
-{
-    const unsigned *w = rows[slot & (ST_WR - 1)] + wid;
-    return ((unsigned long long)w[0] >> 16) | ((unsigned long long)w[1] << 16) | ((unsigned long long)w[2] << 48);
 }
 
 /* k1_finish with the normalisation off the slow path.  The definition stays fx = (float)(n0 / sqrt(L)) with IEEE double sqrt and
@@ -144,16 +138,18 @@ __device__ __forceinline__ void st_finish(const SpDev &d, size_t gi, float px, f
     d.nrm[gi] = make_float4(onx, ony, onz, 0.f);
 }
 
-/* ordered K x K sums of the pixel in ring column t (k1_normal of the tile kernel, read from the gradient ring) */
+/* ordered K x K sums of the pixel in ring column t (k1_normal of the tile kernel, read from the gradient ring): the route of
+ * pixels whose neighbourhood holds a coordinate without the exactness guarantee.  slot_r = ring slot of gradient row r. */
+__device__ __forceinline__ int st_wrap6(int x) { return x >= ST_GR ? x - ST_GR : x; }
 template <int K>
-__device__ __forceinline__ void st_slow_normal(const StSmem &s, const SpDev &d, int t, int nrow /* row r as a band-local index */, size_t gi)
+__device__ __forceinline__ void st_ordered_sums(const StSmem &s, int t, int slot_r, double *sg)
 {
     const int half = K >> 1;
     double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
         double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, ry0 = 0.0, ry1 = 0.0, ry2 = 0.0;
-        const int slot = (nrow - half + a) % ST_GR;
+        const int slot = st_wrap6(st_wrap6(slot_r + ST_GR - half) + a);       /* a < K <= 5: one wrap each */
 #pragma unroll
         for (int b = 0; b < K; ++b) {
             const float4 ga = s.GA[slot][t - half + b];
@@ -163,8 +159,21 @@ __device__ __forceinline__ void st_slow_normal(const StSmem &s, const SpDev &d, 
         }
         sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
     }
-    const float4 pw = d.xyzw[gi];
-    st_finish(d, gi, pw.x, pw.y, pw.z, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
+    sg[0] = sgx0; sg[1] = sgx1; sg[2] = sgx2; sg[3] = sgy0; sg[4] = sgy1; sg[5] = sgy2;
+}
+
+/* sg += sign * gradient element (slot, t) */
+__device__ __forceinline__ void st_acc(const StSmem &s, int slot, int t, double sign, double *sg)
+{
+    const float4 ga = s.GA[slot][t];
+    const float2 gb = s.GB[slot][t];
+    sg[0] += sign * (double)ga.x; sg[1] += sign * (double)ga.y; sg[2] += sign * (double)ga.z;
+    sg[3] += sign * (double)ga.w; sg[4] += sign * (double)gb.x; sg[5] += sign * (double)gb.y;
+}
+__device__ __forceinline__ void st_acc_cs(const StSmem &s, int buf, int t, double *sg)
+{
+    const double2 a = s.CS[buf][0][t], b = s.CS[buf][1][t], c = s.CS[buf][2][t];
+    sg[0] += a.x; sg[1] += a.y; sg[2] += b.x; sg[3] += b.y; sg[4] += c.x; sg[5] += c.y;
 }
 
 __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const __grid_constant__ CUtensorMap tmap, int ns, int SW, int nb, int BR)
@@ -172,7 +181,6 @@ __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const
     extern __shared__ __align__(128) unsigned char st_smem_raw[];
     StSmem &s = *reinterpret_cast<StSmem *>(st_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u, bit = 1u << lane;
     const int W = d.W, H = d.H, N = d.N;
     const float qnan = __int_as_float(0x7fc00000);
     const bool rot = d.R != nullptr;
@@ -190,22 +198,22 @@ __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const
         const int s0 = strip * SW, swid = min(SW, W - s0);
         const int c = s0 - ST_HALO + tid;                                 /* this thread's image column (may lie outside) */
         const bool col_owned = tid >= ST_HALO && tid < ST_HALO + swid;
+        const bool col_inner = c >= 5 && c < W - 5;                       /* PCL's border of 5: no normal outside */
         const int i0 = r0 - ST_HALO;                                      /* first row ingested */
         const int n_ingest = (r1 - r0) + 2 * ST_HALO;
         const int nsteps = (r1 - r0) + ST_HALO + ST_LAG;
-        const size_t fbase = (size_t)f * N;
+        const long long fbase = (long long)f * N;
         float R[9];
         if (rot) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) R[k] = __ldg(d.R + 9 * f + k);
         }
-        /* clear the rings of the previous item */
-        for (int k = tid; k < ST_WR * (ST_NW + 2); k += ST_T) {
-            (&s.hp[0][0])[k] = 0u; (&s.vp[0][0])[k] = 0u; (&s.fa[0][0])[k] = 0u; (&s.fb[0][0])[k] = 0u; (&s.rk[0][0])[k] = 0u; (&s.vm[0][0])[k] = 0u;
-        }
+        /* rings of the previous item: the gradient ring must read zero for rows above the band, the histories start empty */
 #pragma unroll
         for (int k = 0; k < ST_GR; ++k) { s.GA[k][tid] = make_float4(0.f, 0.f, 0.f, 0.f); s.GB[k][tid] = make_float2(0.f, 0.f); }
-        if (tid == 0) { s.nslow[0] = 0; s.nslow[1] = 0; s.anyrisk = 0; }
+        s.hist[0][tid] = 0u; s.hist[1][tid] = 0u;
+        if (tid < 2 * (ST_NW + 1)) (&s.hedge[0][0])[tid] = 0u;
+        if (tid == 0) s.anyrisk = 0;
         if (tid == 0) {                                                   /* rows i0 and i0 + 1 on their way */
             for (int n = 0; n < 2 && n < n_ingest; ++n) {
                 const int slot = (loads + n) % ST_RAW;
@@ -218,115 +226,112 @@ __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const
 
         float z1 = qnan, z2 = qnan;                                       /* levelled z of rows i - 1, i - 2 of this column */
         double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, w4 = 0.0, w5 = 0.0;/* running 5-row column sums of the six gradient channels */
+        unsigned fh = 0, fah = 0, fbh = 0, rkh = 0, vmh = 0;              /* vertical bit histories of this column (bit k = k rows ago) */
+        bool hp1 = false, vp1 = false;                                    /* pair flags hp(i - 2), vp(i - 3) of this column */
         int dirty = 0;                                                    /* risk mode: steps until the column sums are clean again */
         bool riskmode = false;
         float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
         int nvalid = 0, ncrop = 0;
+        float pwx = 0.f, pwy = 0.f, pwz = 0.f;                            /* the levelled point of the pixel finished next (prefetched) */
+        int p6 = 0;                                                       /* n % 6: ring slot of the row ingested in this step */
+        int lslot = loads % ST_RAW, lpar = (loads / ST_RAW) & 1;          /* TMA slot / parity of the row ingested in this step */
+        long long off_i = fbase + (long long)i0 * W + c;                  /* pixel offset of (row i, this column) */
 
         for (int n = 0; n < nsteps; ++n) {
             const int i = i0 + n;                                         /* row ingested in this step */
             if (tid == 0 && n + 2 < n_ingest) {                           /* slot of row i - 1 is free again: row i + 2 */
-                const int slot = (loads + n + 2) % ST_RAW;
+                const int slot = lslot + 2 >= ST_RAW ? lslot + 2 - ST_RAW : lslot + 2;
                 st_mbar_expect(&s.mbar[slot], ST_T * 16);
                 st_tma_row(&tmap, &s.raw[slot][0], &s.mbar[slot], s0 - ST_HALO, i + 2, f);
                 st_tma_row(&tmap, &s.raw[slot][ST_BOX], &s.mbar[slot], s0 - ST_HALO + ST_BOX, i + 2, f);
             }
             riskmode = riskmode || (s.anyrisk != 0);                      /* CTA-uniform: written before the last barrier */
+            const int pb = (n + 1) & 1, cb = n & 1;                       /* buffers written in the previous / in this step */
 
-            /* ---------------------------------------------------------------- D: finish row r */
-            const int r = i - ST_LAG, nr = n - ST_LAG;                    /* nr = band-local index of row r (slot arithmetic) */
-            const bool fin = r >= r0 && r < r1;                           /* CTA-uniform */
-            if (fin) {
-                /* smoothing window per pixel (PCL's 1.0 / 1.4 chamfer map, capped at 5) from bit rows: lanes 0..8 take the flag
-                 * rows r - 4 .. r + 4, lanes 9..13 the gradient rows r - 2 .. r + 2, lanes 14..20 the risk rows r - 3 .. r + 3; the
-                 * per-row contributions are OR-reduced across the warp.  A flagged pixel at row distance a and column distance h
-                 * allows a window of kcat[a][h] (see k_ingest_normals, S3). */
-                unsigned cz0 = 0, cz2 = 0, cz3 = 0, cz4 = 0, ca5 = 0, ca4 = 0, ca3 = 0, ca2 = 0, cb5 = 0, cb4 = 0, cb3 = 0, cb2 = 0, cwr = 0;
-                if (lane < 9) {
-                    const int q = nr - 4 + lane, dd = lane < 4 ? 4 - lane : lane - 4;
-                    const unsigned long long hq = st_local(s.hp, q, wid), vq = st_local(s.vp, q, wid), vm1 = st_local(s.vp, q - 1, wid);
-                    unsigned long long D0 = hq | (hq << 1) | vq | vm1;
-                    unsigned long long D1 = D0 | (D0 << 1) | (D0 >> 1);
-                    unsigned long long D2 = D1 | (D1 << 1) | (D1 >> 1);
-                    unsigned long long D3 = D2 | (D2 << 1) | (D2 >> 1);
-                    unsigned long long D4 = D3 | (D3 << 1) | (D3 >> 1);
-                    const unsigned e0 = (unsigned)(D0 >> 16), e1 = (unsigned)(D1 >> 16), e2 = (unsigned)(D2 >> 16), e3 = (unsigned)(D3 >> 16), e4 = (unsigned)(D4 >> 16);
-                    cz0 = dd == 0 ? e2 : dd == 1 ? e1 : dd == 2 ? e0 : 0u;
-                    cz2 = dd <= 2 ? e2 : 0u;
-                    cz3 = dd <= 2 ? e3 : dd == 3 ? e2 : 0u;
-                    cz4 = dd <= 2 ? e4 : dd == 3 ? e3 : e2;
-                } else if (lane < 14) {
-                    const int a = lane - 9, q = nr - 2 + a;               /* gradient row offset a - 2 */
-                    const unsigned long long A = st_local(s.fa, q, wid), Bq = st_local(s.fb, q, wid);
-                    const unsigned long long A3 = (A << 1) | A | (A >> 1), B3 = (Bq << 1) | Bq | (Bq >> 1);
-                    const unsigned a5 = (unsigned)((A3 | (A << 2) | (A >> 2)) >> 16), b5 = (unsigned)((B3 | (Bq << 2) | (Bq >> 2)) >> 16);
-                    const unsigned a4 = (unsigned)((A3 | (A << 2)) >> 16), b4 = (unsigned)((B3 | (Bq << 2)) >> 16);
-                    const unsigned a3 = (unsigned)(A3 >> 16), b3 = (unsigned)(B3 >> 16);
-                    const unsigned a2 = (unsigned)(((A << 1) | A) >> 16), b2 = (unsigned)(((Bq << 1) | Bq) >> 16);
-                    ca5 = a5; cb5 = b5;
-                    if (a <= 3) { ca4 = a4; cb4 = b4; }
-                    if (a >= 1 && a <= 3) { ca3 = a3; cb3 = b3; }
-                    if (a >= 1 && a <= 2) { ca2 = a2; cb2 = b2; }
-                } else if (lane < 21 && riskmode) {
-                    const unsigned long long K0 = st_local(s.rk, nr - 3 + (lane - 14), wid);
-                    const unsigned long long K1 = K0 | (K0 << 1) | (K0 >> 1), K2 = K1 | (K1 << 1) | (K1 >> 1), K3 = K2 | (K2 << 1) | (K2 >> 1);
-                    cwr = (unsigned)(K3 >> 16);
-                }
-                const unsigned z0 = __reduce_or_sync(0xffffffffu, cz0), zz2 = __reduce_or_sync(0xffffffffu, cz2), z3 = __reduce_or_sync(0xffffffffu, cz3),
-                               z4 = __reduce_or_sync(0xffffffffu, cz4);
-                const unsigned wn5 = __reduce_or_sync(0xffffffffu, ca5) & __reduce_or_sync(0xffffffffu, cb5);
-                const unsigned wn4 = __reduce_or_sync(0xffffffffu, ca4) & __reduce_or_sync(0xffffffffu, cb4);
-                const unsigned wn3 = __reduce_or_sync(0xffffffffu, ca3) & __reduce_or_sync(0xffffffffu, cb3);
-                const unsigned wn2 = __reduce_or_sync(0xffffffffu, ca2) & __reduce_or_sync(0xffffffffu, cb2);
-                const unsigned wrisk = riskmode ? __reduce_or_sync(0xffffffffu, cwr) : 0u;
-                const unsigned v = s.vm[nr & (ST_WR - 1)][wid + 1];
-                const unsigned k5 = v & wn5 & ~z4, k4 = v & wn4 & (z4 & ~z3), k3 = v & wn3 & (z3 & ~zz2), k2 = v & wn2 & (zz2 & ~z0);
-                const int kk = (k5 & bit) ? 5 : (k4 & bit) ? 4 : (k3 & bit) ? 3 : (k2 & bit) ? 2 : 0;
-                const bool fast = kk == 5 && !(wrisk & bit);
-                const bool slow = col_owned && kk != 0 && !fast;
-                const size_t gi = fbase + (size_t)r * W + c;
-                if (col_owned) {
-                    if (fast) {
-                        const double2 a0 = s.CS[0][tid - 2], a1 = s.CS[0][tid - 1], a2 = s.CS[0][tid + 1], a3 = s.CS[0][tid + 2];
-                        const double2 b0 = s.CS[1][tid - 2], b1 = s.CS[1][tid - 1], b2 = s.CS[1][tid + 1], b3 = s.CS[1][tid + 2];
-                        const double2 c0 = s.CS[2][tid - 2], c1 = s.CS[2][tid - 1], c2 = s.CS[2][tid + 1], c3 = s.CS[2][tid + 2];
-                        const double g0 = ((a0.x + a1.x) + w0) + (a2.x + a3.x), g1 = ((a0.y + a1.y) + w1) + (a2.y + a3.y);
-                        const double g2 = ((b0.x + b1.x) + w2) + (b2.x + b3.x), g3 = ((b0.y + b1.y) + w3) + (b2.y + b3.y);
-                        const double g4 = ((c0.x + c1.x) + w4) + (c2.x + c3.x), g5 = ((c0.y + c1.y) + w5) + (c2.y + c3.y);
-                        const float4 pw = d.xyzw[gi];                     /* this thread stored it seven steps ago */
-                        st_finish(d, gi, pw.x, pw.y, pw.z, g0, g1, g2, g3, g4, g5);
-                    } else if (!slow) d.nrm[gi] = make_float4(qnan, qnan, qnan, 0.f);
-                }
-                const unsigned bs = __ballot_sync(0xffffffffu, slow);
-                if (bs) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s.nslow[n & 1], __popc(bs));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (slow) s.slow[n & 1][base + __popc(bs & lt)] = (unsigned short)(tid | (kk << 12));
+            /* ---------------------------------------------------------------- D: finish row r = i - 7 */
+            const int r = i - ST_LAG;
+            if (r >= r0 && r < r1 && col_owned) {
+                /* smoothing window (PCL's 1.0 / 1.4 chamfer map capped at 5; kcat[a][h] of k_ingest_normals, S3) from the bit
+                 * histories of the columns c - 4 .. c + 4: f_h = depth-change flags of rows r - 4 .. r + 4 (bit 4 - a) at column
+                 * distance h, either side */
+                const unsigned *hs = s.hist[pb] + tid;
+                const unsigned h0 = hs[0], l1 = hs[-1], r1_ = hs[1], l2 = hs[-2], r2 = hs[2], l3 = hs[-3], r3 = hs[3], l4 = hs[-4], r4 = hs[4];
+                const unsigned c1 = h0 | l1 | r1_, c2 = c1 | l2 | r2, c3 = c2 | l3 | r3, c4 = c3 | l4 | r4;   /* cumulative over |h| */
+                const bool z0 = ((c2 & 0x010u) | (c1 & 0x028u) | (h0 & 0x044u)) != 0;
+                const bool zz2 = (c2 & 0x07cu) != 0;
+                const bool z3 = ((c3 & 0x07cu) | (c2 & 0x082u)) != 0;
+                const bool z4 = ((c4 & 0x07cu) | (c3 & 0x082u) | (c2 & 0x101u)) != 0;
+                /* one finite element in each gradient window (PCL's finite-element counts): rows r - 2 .. r + 2 = bits 4 .. 0 of the
+                 * fa / fb fields; windows: 5 = rows -2..2, cols -2..2; 4 = rows -2..1, cols -2..1; 3 = rows / cols -1..1; 2 = -1..0 */
+                const unsigned u2 = l1 | h0, u3 = u2 | r1_, u4 = u3 | l2, u5 = u4 | r2;
+                const bool wn5 = (u5 & (0x1fu << ST_H_FA)) && (u5 & (0x1fu << ST_H_FB));
+                const bool wn4 = (u4 & (0x1eu << ST_H_FA)) && (u4 & (0x1eu << ST_H_FB));
+                const bool wn3 = (u3 & (0x0eu << ST_H_FA)) && (u3 & (0x0eu << ST_H_FB));
+                const bool wn2 = (u2 & (0x0cu << ST_H_FA)) && (u2 & (0x0cu << ST_H_FB));
+                const bool v = (vmh >> 6) & 1u;
+                const int kk = !v ? 0 : (wn5 && !z4) ? 5 : (wn4 && z4 && !z3) ? 4 : (wn3 && z3 && !zz2) ? 3 : (wn2 && zz2 && !z0) ? 2 : 0;
+                /* an inexact coordinate within three pixels: rows r - 3 .. r + 3 = bits 3 .. 9 of the risk field */
+                const bool wrisk = riskmode && (((c3) & (0x3f8u << ST_H_RK)) != 0);
+                const long long gi = off_i - (long long)ST_LAG * W;
+                if (kk == 0) d.nrm[gi] = make_float4(qnan, qnan, qnan, 0.f);
+                else {
+                    double sg[6];
+                    const int gslot = st_wrap6(p6 + 5);                   /* ring slot of gradient row r (n - 7 = n + 5 mod 6) */
+                    if (wrisk) {
+                        if (kk == 5) st_ordered_sums<5>(s, tid, gslot, sg);
+                        else if (kk == 4) st_ordered_sums<4>(s, tid, gslot, sg);
+                        else if (kk == 3) st_ordered_sums<3>(s, tid, gslot, sg);
+                        else st_ordered_sums<2>(s, tid, gslot, sg);
+                    } else if (kk == 5) {
+                        const double2 a0 = s.CS[pb][0][tid - 2], a1 = s.CS[pb][0][tid - 1], a2 = s.CS[pb][0][tid + 1], a3 = s.CS[pb][0][tid + 2];
+                        const double2 b0 = s.CS[pb][1][tid - 2], b1 = s.CS[pb][1][tid - 1], b2 = s.CS[pb][1][tid + 1], b3 = s.CS[pb][1][tid + 2];
+                        const double2 e0 = s.CS[pb][2][tid - 2], e1 = s.CS[pb][2][tid - 1], e2 = s.CS[pb][2][tid + 1], e3 = s.CS[pb][2][tid + 2];
+                        sg[0] = ((a0.x + a1.x) + w0) + (a2.x + a3.x); sg[1] = ((a0.y + a1.y) + w1) + (a2.y + a3.y);
+                        sg[2] = ((b0.x + b1.x) + w2) + (b2.x + b3.x); sg[3] = ((b0.y + b1.y) + w3) + (b2.y + b3.y);
+                        sg[4] = ((e0.x + e1.x) + w4) + (e2.x + e3.x); sg[5] = ((e0.y + e1.y) + w5) + (e2.y + e3.y);
+                    } else {
+                        /* windows of 4, 3, 2 with the exactness guarantee: every partial sum is exact, so the order is free.  The
+                         * 5-row column sums minus the rows the window leaves out, or the 2 x 2 elements directly */
+                        sg[0] = sg[1] = sg[2] = sg[3] = sg[4] = sg[5] = 0.0;
+                        if (kk == 4) {                                    /* rows r - 2 .. r + 1, columns c - 2 .. c + 1 */
+                            const int below = st_wrap6(gslot + 2);
+                            sg[0] = w0; sg[1] = w1; sg[2] = w2; sg[3] = w3; sg[4] = w4; sg[5] = w5;
+                            st_acc_cs(s, pb, tid - 2, sg); st_acc_cs(s, pb, tid - 1, sg); st_acc_cs(s, pb, tid + 1, sg);
+                            st_acc(s, below, tid - 2, -1.0, sg); st_acc(s, below, tid - 1, -1.0, sg); st_acc(s, below, tid, -1.0, sg); st_acc(s, below, tid + 1, -1.0, sg);
+                        } else if (kk == 3) {                             /* rows r - 1 .. r + 1, columns c - 1 .. c + 1 */
+                            const int above = st_wrap6(gslot + ST_GR - 2), below = st_wrap6(gslot + 2);
+                            sg[0] = w0; sg[1] = w1; sg[2] = w2; sg[3] = w3; sg[4] = w4; sg[5] = w5;
+                            st_acc_cs(s, pb, tid - 1, sg); st_acc_cs(s, pb, tid + 1, sg);
+                            for (int b = -1; b <= 1; ++b) { st_acc(s, above, tid + b, -1.0, sg); st_acc(s, below, tid + b, -1.0, sg); }
+                        } else {                                          /* rows r - 1 .. r, columns c - 1 .. c */
+                            const int up = st_wrap6(gslot + ST_GR - 1);
+                            st_acc(s, up, tid - 1, 1.0, sg); st_acc(s, up, tid, 1.0, sg); st_acc(s, gslot, tid - 1, 1.0, sg); st_acc(s, gslot, tid, 1.0, sg);
+                        }
+                    }
+                    st_finish(d, (size_t)gi, pwx, pwy, pwz, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
                 }
             }
-            __syncthreads();                                              /* column sums read; the row's slow list is complete */
 
-            /* ---------------------------------------------------------------- E: ordered sums of the listed pixels of row r */
-            if (fin) {
-                const int nsl = s.nslow[n & 1];
-                if (tid == 0) s.nslow[(n + 1) & 1] = 0;
-                for (int u = tid; u < nsl; u += ST_T) {
-                    const int code = s.slow[n & 1][u], t = code & 0xfff, kk = code >> 12;
-                    const size_t gi = fbase + (size_t)r * W + (s0 - ST_HALO + t);
-                    if (kk == 5) st_slow_normal<5>(s, d, t, nr, gi);
-                    else if (kk == 4) st_slow_normal<4>(s, d, t, nr, gi);
-                    else if (kk == 3) st_slow_normal<3>(s, d, t, nr, gi);
-                    else st_slow_normal<2>(s, d, t, nr, gi);
-                }
+            /* ---------------------------------------------------------------- B: depth-change pair flags (on the levelled z: the reference's quirk) */
+            {
+                /* hp(i - 1): this column against its right neighbour; vp(i - 2): row i - 2 against row i - 1.  The flag of pixel
+                 * (i - 2, c) is complete now: hp(i - 2) of this column and of the left neighbour, vp(i - 2), vp(i - 3) */
+                const float zr = tid + 1 < ST_T ? s.P[st_wrap6(p6 + 5)][tid + 1].z : qnan;
+                const bool hpn = n >= 1 && k1_bad_pair(z1, zr);
+                const bool vpn = n >= 2 && k1_bad_pair(z2, z1);
+                bool hl = __shfl_up_sync(0xffffffffu, hp1, 1);
+                if (lane == 0) hl = s.hedge[pb][wid] != 0;                /* the left warp's last lane, one step ago */
+                if (lane == 31) s.hedge[cb][wid + 1] = hpn ? 1u : 0u;
+                fh = ((fh << 1) | ((hp1 | hl | vpn | vp1) ? 1u : 0u)) & 0x1ffu;
+                hp1 = hpn; vp1 = vpn;
             }
 
             /* ---------------------------------------------------------------- A: ingest row i */
             float z0n = qnan;
+            bool risk = false, vmn = false;
             if (n < n_ingest) {
-                const int slot = (loads + n) % ST_RAW;
-                st_mbar_wait(&s.mbar[slot], (unsigned)(((loads + n) / ST_RAW) & 1));
-                const float4 p = s.raw[slot][tid];
+                st_mbar_wait(&s.mbar[lslot], (unsigned)lpar);
+                const float4 p = s.raw[lslot][tid];
                 float ox = p.x, oy = p.y, oz = p.z;
                 if (rot) {
                     if (!isnan(p.x)) {
@@ -335,12 +340,11 @@ __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const
                         oz = R[6] * p.x + R[7] * p.y + R[8] * p.z;
                     } else { ox = oy = oz = qnan; }
                 }
-                /* remove_nan_points: r, g or b == 0 marks an invalid pixel; pixels outside the image arrive as NaN */
-                if (__vcmpeq4(__float_as_uint(p.w) | 0xff000000u, 0u) || i < 0 || i >= H || c < 0 || c >= W) { ox = oy = oz = qnan; }
-                const bool own = col_owned && i >= r0 && i < r1;
+                /* remove_nan_points: r, g or b == 0 marks an invalid pixel; pixels outside the image arrive as NaN records */
+                if (__vcmpeq4(__float_as_uint(p.w) | 0xff000000u, 0u)) { ox = oy = oz = qnan; }
                 bool crop = false;
-                if (own) {
-                    d.xyzw[fbase + (size_t)i * W + c] = make_float4(ox, oy, oz, 0.f);
+                if (col_owned && i >= r0 && i < r1) {
+                    d.xyzw[off_i] = make_float4(ox, oy, oz, 0.f);
                     if (sp_finite3(ox, oy, oz)) {
                         ++nvalid;
                         if (!(ox < d.c.x0 || ox > d.c.x1) && !(oy < d.c.y0 || oy > d.c.y1) && !(oz < d.c.z0 || oz > d.c.z1)) {
@@ -350,60 +354,50 @@ __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const
                         }
                     }
                 }
-                s.P[n % ST_PR][tid] = make_float4(ox, oy, oz, 0.f);
+                s.P[p6][tid] = make_float4(ox, oy, oz, 0.f);
                 z0n = oz;
-                const bool risk = k1_inexact_risk(ox) | k1_inexact_risk(oy) | k1_inexact_risk(oz);
-                const unsigned brk = __ballot_sync(0xffffffffu, risk);
-                const unsigned bvm = __ballot_sync(0xffffffffu, i >= 5 && i < H - 5 && c >= 5 && c < W - 5 && sp_finite(oz));
+                risk = k1_inexact_risk(ox) | k1_inexact_risk(oy) | k1_inexact_risk(oz);
+                vmn = col_inner && i >= 5 && i < H - 5 && sp_finite(oz);
+                if (risk) s.anyrisk = 1;
                 const unsigned bc = __ballot_sync(0xffffffffu, crop);
-                if (lane == 0) {
-                    s.rk[n & (ST_WR - 1)][wid + 1] = brk; s.vm[n & (ST_WR - 1)][wid + 1] = bvm;
-                    if (brk) s.anyrisk = 1;
-                    if (bc) {                                             /* cropped pixels per 1024-pixel block, for the voxel stage */
-                        const int p0 = i * W + (c - lane + 0), left = 1024 - (p0 & 1023);
-                        const unsigned lo = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-                        int *vc = d.vcnt + (size_t)f * d.nblk + (p0 >> 10);
-                        if (bc & lo) atomicAdd(vc, __popc(bc & lo));
-                        if (bc & ~lo) atomicAdd(vc + 1, __popc(bc & ~lo));
-                    }
+                if (lane == 0 && bc) {                                    /* cropped pixels per 1024-pixel block, for the voxel stage */
+                    const int p0 = i * W + c, left = 1024 - (p0 & 1023);
+                    const unsigned lo = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+                    int *vc = d.vcnt + (size_t)f * d.nblk + (p0 >> 10);
+                    if (bc & lo) atomicAdd(vc, __popc(bc & lo));
+                    if (bc & ~lo) atomicAdd(vc + 1, __popc(bc & ~lo));
                 }
             }
-
-            /* ---------------------------------------------------------------- B: depth-change pair flags (on the levelled z: the reference's quirk) */
-            if (n >= 1) {
-                const float zr = tid + 1 < ST_T ? s.P[(n - 1) % ST_PR][tid + 1].z : qnan;
-                const unsigned bh = __ballot_sync(0xffffffffu, k1_bad_pair(z1, zr));
-                if (lane == 0) s.hp[(n - 1) & (ST_WR - 1)][wid + 1] = bh;
-            }
-            if (n >= 2) {
-                const unsigned bv = __ballot_sync(0xffffffffu, k1_bad_pair(z2, z1));
-                if (lane == 0) s.vp[(n - 2) & (ST_WR - 1)][wid + 1] = bv;
-            }
+            rkh = ((rkh << 1) | (risk ? 1u : 0u)) & 0x3ffu;
+            vmh = (vmh << 1) | (vmn ? 1u : 0u);
             z2 = z1; z1 = z0n;
 
             /* ---------------------------------------------------------------- C: gradients of row j = i - 4, column sums of centre row i - 6 */
-            const int j = i - 4, nj = n - 4;
+            const int j = i - 4;
+            bool fa = false, fb = false;
             if (j >= r0 - 2 && j <= r1 + 1) {                             /* CTA-uniform */
+                const int pj = st_wrap6(p6 + 2), gj = pj;                 /* ring slots of row j (n - 4 = n + 2 mod 6) */
                 const int tl = tid > 0 ? tid - 1 : 0, tr = tid + 1 < ST_T ? tid + 1 : ST_T - 1;
-                const float4 L = s.P[nj % ST_PR][tl], Rr = s.P[nj % ST_PR][tr], U = s.P[(nj - 1) % ST_PR][tid], Dn = s.P[(nj + 1) % ST_PR][tid];
+                const float4 L = s.P[pj][tl], Rr = s.P[pj][tr], U = s.P[st_wrap6(p6 + 1)][tid], Dn = s.P[st_wrap6(p6 + 3)][tid];
                 const float ax = Rr.x - L.x, ay = Rr.y - L.y, az = Rr.z - L.z;
                 const float bx = Dn.x - U.x, by = Dn.y - U.y, bz = Dn.z - U.z;
-                const bool fa = sp_finite(ax + (ay + az)), fb = sp_finite(bx + (by + bz));
+                fa = sp_finite(ax + (ay + az)); fb = sp_finite(bx + (by + bz));
                 const float g0 = fa ? ax : 0.0f, g1 = fa ? ay : 0.0f, g2 = fa ? az : 0.0f, g3 = fb ? bx : 0.0f, g4 = fb ? by : 0.0f, g5 = fb ? bz : 0.0f;
-                const float4 oa = s.GA[(nj + 1) % ST_GR][tid];            /* row j - 5 (zero before the band's first gradient row) */
-                const float2 ob = s.GB[(nj + 1) % ST_GR][tid];
-                s.GA[nj % ST_GR][tid] = make_float4(g0, g1, g2, g3);
-                s.GB[nj % ST_GR][tid] = make_float2(g4, g5);
-                const unsigned ba = __ballot_sync(0xffffffffu, fa), bb = __ballot_sync(0xffffffffu, fb);
-                if (lane == 0) { s.fa[nj & (ST_WR - 1)][wid + 1] = ba; s.fb[nj & (ST_WR - 1)][wid + 1] = bb; }
+                const float4 oa = s.GA[st_wrap6(gj + 1)][tid];            /* row j - 5 (zero before the band's first gradient row) */
+                const float2 ob = s.GB[st_wrap6(gj + 1)][tid];
+                s.GA[gj][tid] = make_float4(g0, g1, g2, g3);
+                s.GB[gj][tid] = make_float2(g4, g5);
                 bool rebuild = false;
                 if (riskmode) {
                     /* an inexact element poisons this column's running sums until it has left the window: five steps later the
-                     * sums are rebuilt from the ring (all clean again); pixels that would use a poisoned sum are on the slow list
-                     * (risk within three pixels), so nothing reads it in between */
-                    const unsigned long long K0 = st_local(s.rk, nj - 1, wid) | st_local(s.rk, nj, wid) | st_local(s.rk, nj + 1, wid);
-                    const unsigned near = (unsigned)((K0 | (K0 << 1) | (K0 >> 1)) >> 16);
-                    if (near & bit) dirty = 6;
+                     * sums are rebuilt from the ring (all clean again); pixels that would use a poisoned sum take the ordered sums
+                     * (risk within three pixels), so nothing reads it in between.  Risk rows j - 1 .. j + 1 = bits 5 .. 3 of the
+                     * risk histories (this step's included), columns c - 1 .. c + 1 */
+                    const unsigned mine = rkh & 0x38u;
+                    const unsigned lft = __shfl_up_sync(0xffffffffu, mine, 1), rgt = __shfl_down_sync(0xffffffffu, mine, 1);
+                    const unsigned nl = (s.hist[pb][tl] >> ST_H_RK) & 0x1cu, nr_ = (s.hist[pb][tr] >> ST_H_RK) & 0x1cu;   /* one step old: bits 4 .. 2 */
+                    const bool near = (mine | (lane > 0 ? lft : nl << 1) | (lane < 31 ? rgt : nr_ << 1)) != 0;
+                    if (near) dirty = 6;
                     if (dirty > 0) { --dirty; rebuild = dirty == 0; }
                 }
                 if (!rebuild) {
@@ -411,14 +405,25 @@ __global__ void __launch_bounds__(ST_T, 2) k_ingest_normals_strip(SpDev d, const
                     w0 -= (double)oa.x; w1 -= (double)oa.y; w2 -= (double)oa.z; w3 -= (double)oa.w; w4 -= (double)ob.x; w5 -= (double)ob.y;
                 } else {
                     w0 = (double)g0; w1 = (double)g1; w2 = (double)g2; w3 = (double)g3; w4 = (double)g4; w5 = (double)g5;
-                    for (int a = 1; a < 5; ++a) {                         /* rows j - 1 .. j - 4 (zero rows before the band count as zero) */
-                        const float4 qa = s.GA[(nj - a + ST_GR) % ST_GR][tid];
-                        const float2 qb = s.GB[(nj - a + ST_GR) % ST_GR][tid];
+                    for (int a = 1; a < 5; ++a) {                         /* rows j - 1 .. j - 4 (rows above the band read zero) */
+                        const float4 qa = s.GA[st_wrap6(gj + ST_GR - a)][tid];
+                        const float2 qb = s.GB[st_wrap6(gj + ST_GR - a)][tid];
                         w0 += (double)qa.x; w1 += (double)qa.y; w2 += (double)qa.z; w3 += (double)qa.w; w4 += (double)qb.x; w5 += (double)qb.y;
                     }
                 }
-                s.CS[0][tid] = make_double2(w0, w1); s.CS[1][tid] = make_double2(w2, w3); s.CS[2][tid] = make_double2(w4, w5);
+                s.CS[cb][0][tid] = make_double2(w0, w1); s.CS[cb][1][tid] = make_double2(w2, w3); s.CS[cb][2][tid] = make_double2(w4, w5);
             }
+            fah = ((fah << 1) | (fa ? 1u : 0u)) & 0x1fu;
+            fbh = ((fbh << 1) | (fb ? 1u : 0u)) & 0x1fu;
+            s.hist[cb][tid] = fh | (fah << ST_H_FA) | (fbh << ST_H_FB) | (rkh << ST_H_RK);
+            /* the point of the pixel this thread finishes in the next step (row i - 6): it stored it six steps ago */
+            if (col_owned && i - 6 >= r0 && i - 6 < r1) {
+                const float4 pw = d.xyzw[off_i - 6LL * W];
+                pwx = pw.x; pwy = pw.y; pwz = pw.z;
+            }
+            off_i += W;
+            p6 = p6 + 1 == ST_PR ? 0 : p6 + 1;
+            if (n < n_ingest) { if (++lslot == ST_RAW) { lslot = 0; lpar ^= 1; } }
             __syncthreads();
         }
         loads += n_ingest;
