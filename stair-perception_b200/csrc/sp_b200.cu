@@ -129,7 +129,9 @@ struct sp_ctx {
     /* depth-image ingest (sp_process_depth_frames): staging buffers, allocated on first use */
     void *d_depth[2] = { nullptr, nullptr }; unsigned char *d_color[2] = { nullptr, nullptr };
     float *d_maps = nullptr;                 /* colmap[W] then rowmap[H] */
-    /* K1K2: the row-marching TMA kernel (sp_strip.cuh) unless SP_K1=tile or the driver has no tensor-map encoder */
+    /* K1K2 variant: 0 = tile kernel with plain loads (k_ingest_normals), 1 = the row-marching TMA kernel (sp_strip.cuh),
+     * 2 = tile kernel fed by one TMA tensor copy per tile (k_ingest_normals_tma).  SP_K1 = tile | strip | tma picks one. */
+    int k1_variant = 2;
     bool use_strip = true;
     int num_sms = 148;
     void *encode_tiled = nullptr;            /* cuTensorMapEncodeTiled, through the runtime's driver entry point */
@@ -200,7 +202,22 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     if ((all || only_stage == 0) && ctx->normal_mode == 0) {
         k_init_frames<<<(nB * SP_NCOUNT + 255) / 256, 256, 0, st>>>(d, nB);
         mark(ctx, "k_init_frames");
-        if (ctx->use_strip && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0) {
+        const bool can_tma = ctx->encode_tiled != nullptr && (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
+        if (ctx->k1_variant == 2 && can_tma) {
+            typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                          const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            CUtensorMap tmap;
+            const cuuint64_t dims[4] = { 4, (cuuint64_t)ctx->W, (cuuint64_t)ctx->H, (cuuint64_t)nB };
+            const cuuint64_t strides[3] = { 16, (cuuint64_t)ctx->W * 16, (cuuint64_t)N * 16 };
+            const cuuint32_t box[4] = { 4, K1_RW, K1_RH, 1 }, estr[4] = { 1, 1, 1, 1 };
+            const CUresult cr = reinterpret_cast<encode_fn>(ctx->encode_tiled)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float4 *>(d_in), dims, strides, box, estr,
+                                                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+            if (cr != CUDA_SUCCESS) { ERR(ctx) = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return SP_ERR_CUDA; }
+            dim3 g((ctx->W + K1_TW - 1) / K1_TW, (ctx->H + K1_TH - 1) / K1_TH, nB);
+            k_ingest_normals_tma<<<g, K1_THREADS, sizeof(K1Smem), st>>>(d, tmap);
+            mark(ctx, "k_ingest_normals");
+        } else if (ctx->k1_variant == 1 && can_tma) {
             /* one tensor map per chunk: {4 floats, W, H, frames} over the caller's records; a box is half a strip row */
             typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                           const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -462,15 +479,18 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     for (int i = 0; i < 2; ++i) if ((e = cudaEventCreateWithFlags(&ctx->ev_res[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(k_ingest_normals_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StSmem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
     (void)cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     {
         const char *t = getenv("SP_K1");
-        ctx->use_strip = !(t && std::string(t) == "tile");       /* default: the strip kernel */
+        const std::string want = t ? t : "";
+        ctx->k1_variant = want == "tile" ? 0 : want == "strip" ? 1 : 2;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess ||
-            !ctx->encode_tiled) { (void)cudaGetLastError(); ctx->encode_tiled = nullptr; ctx->use_strip = false; }
+            !ctx->encode_tiled) { (void)cudaGetLastError(); ctx->encode_tiled = nullptr; ctx->k1_variant = 0; }
     }
     *out = ctx;
     return SP_OK;

@@ -16,11 +16,15 @@ import importlib  # noqa: E402
 synth = importlib.import_module("stair_perception_b200.synth")
 
 
-def ctx_pair(w, h, b, params=None):
+VARIANT = os.environ.get("K1_VARIANT", "tma")             # the variant compared against the plain tile kernel
+
+
+def ctx_pair(w, h, b, params=None, variant=None):
     os.environ["SP_K1"] = "tile"
     a = sp.Context(params, device=0, width=w, height=h, max_batch=b)
-    del os.environ["SP_K1"]
+    os.environ["SP_K1"] = variant or VARIANT
     n = sp.Context(params, device=0, width=w, height=h, max_batch=b)
+    del os.environ["SP_K1"]
     return a, n
 
 
@@ -33,7 +37,7 @@ def diff(name, clouds, R, w, h, params=None, show=1):
     for f in range(nf):
         for k in ("status", "n_valid", "n_crop"):
             if int(ro[f][k]) != int(rn[f][k]):
-                print("  %s frame %d %s: tile %d strip %d" % (name, f, k, int(ro[f][k]), int(rn[f][k])))
+                print("  %s frame %d %s: tile %d other %d" % (name, f, k, int(ro[f][k]), int(rn[f][k])))
                 bad += 1
         for tap in ("xyz", "normals", "minmax"):
             a, b = old.tap(f, tap), new.tap(f, tap)
@@ -89,8 +93,11 @@ def main():
     d_c = base.repeat(8, 1).contiguous()
     d_R = torch.from_numpy(np.stack([f[1] for f in fr])).cuda().repeat(8, 1).contiguous()
     torch.cuda.synchronize()
-    old, new = ctx_pair(512, 424, 256)
-    for nm, c in (("tile", old), ("strip", new)):
+    old, new = ctx_pair(512, 424, 256, variant="tma")
+    os.environ["SP_K1"] = "strip"
+    third = sp.Context(device=0, width=512, height=424, max_batch=256)
+    del os.environ["SP_K1"]
+    for nm, c in (("tile", old), ("tma", new), ("strip", third)):
         ts = []
         for it in range(8):
             c.run_stage_device(d_c.data_ptr(), d_R.data_ptr(), 256, 0)
