@@ -5,6 +5,7 @@
 #include "sp_common.cuh"
 #include "sp_front.cuh"
 #include "sp_strip.cuh"
+#include "sp_voxel.cuh"
 #include "sp_seg.cuh"
 #include "sp_knn.cuh"
 #include "sp_stair.h"
@@ -121,8 +122,7 @@ struct sp_ctx {
     /* per-kernel trace of the last chunk (SP_TRACE=1 or sp_set_trace): one event after every launch */
     /* a3' kNN normals (unorganised clouds): allocated on first use */
     int normal_mode = 0;
-    std::vector<int> h_foff;                  /* host copy of foff (one read per chunk) */
-    bool force_key64 = false;                 /* SP_KEY64=1: always the 64-bit voxel sort (parity tests of that path) */
+    int force_vbits = 0;                      /* SP_VBITS=n: sort at least n key bits (32 = the four-pass path of wrapped voxel indices) */
     int *knn_mm = nullptr, *knn_bstart = nullptr, *knn_bend = nullptr;
     SpKnnGrid *knn_grid = nullptr;
     float4 *knn_pts = nullptr;
@@ -271,54 +271,10 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     CK(cudaEventRecord(ctx->ev[1], st));
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
     if (want_voxel) {
-        k_frame_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, nB);
-        k_voxel_offsets<<<nB, 256, 0, st>>>(d);
-        k_frame_offsets<<<1, 1024, 0, st>>>(d, nB);
-        mark(ctx, "k_frame_grid+offsets");
-        /* the one host round trip of a chunk: where each frame's cropped points sit in the sort arrays, and how many bits the
-         * largest voxel grid of the chunk needs */
-        std::vector<int> &fo = ctx->h_foff;
-        fo.resize((size_t)nB + 2);
-        CK(cudaMemcpyAsync(fo.data(), d.foff, sizeof(int) * ((size_t)nB + 2), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const int total = fo[nB];
-        int vbits = 1;                                                       /* 0x7fffffff = some frame's indices wrapped: 32 bits */
-        while (vbits < 32 && (fo[nB + 1] == 0x7fffffff || (1LL << vbits) < (long long)fo[nB + 1])) ++vbits;
-        const int room = 1 << std::min(30, 32 - vbits);                      /* frames that fit beside the voxel bits in 32 bits */
-        d.key32 = (room >= 32 || room >= nB) ? 1 : 0;
-        if (ctx->force_key64) d.key32 = 0;
-        d.vbits = vbits;
-        d.fgroup = 1;
-        while (d.fgroup < nB && d.fgroup < room) d.fgroup <<= 1;
-        ctx->d.key32 = d.key32; ctx->d.vbits = d.vbits; ctx->d.fgroup = d.fgroup;
-        k_voxel_key<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
-        mark(ctx, "k_voxel_key");
-        int nsort = 0;
-        if (total > 0 && d.key32) {
-            /* stable LSD sort of (frame-in-group, voxel index) keys: ceil((vbits + log2 fgroup) / 8) passes of 8 B per point */
-            int gbits = 0;
-            while ((1 << gbits) < d.fgroup) ++gbits;
-            for (int g0 = 0; g0 < nB; g0 += d.fgroup) {
-                const int o0 = fo[g0], o1 = fo[std::min(nB, g0 + d.fgroup)];
-                if (o1 <= o0) continue;
-                size_t tb = ctx->cub_bytes;
-                CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, reinterpret_cast<unsigned *>(d.key_a) + o0, reinterpret_cast<unsigned *>(d.key_b) + o0,
-                                                   d.val_a + o0, d.val_b + o0, (size_t)(o1 - o0), 0, std::min(32, vbits + gbits), st));
-                nsort += 2 + (std::min(32, vbits + gbits) + 7) / 8;
-            }
-        } else if (total > 0) {
-            size_t tb = ctx->cub_bytes;
-            CK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, tb, d.key_a, d.key_b, d.val_a, d.val_b, (size_t)total, 0, 32 + frame_bits(nB), st));
-            nsort = 2 + (32 + frame_bits(nB) + 7) / 8;
-        }
-        mark(ctx, "radix_sort");
-        k_voxel_pick<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
-        mark(ctx, "k_voxel_pick");
-        k_scan_blocks<<<nB, 256, 0, st>>>(d);
-        mark(ctx, "k_scan_blocks");
-        k_scatter_lists<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
-        mark(ctx, "k_scatter_lists");
-        ctx->launches += 7 + nsort;
+        /* the whole voxel stage of a frame in one CTA: grid, keys, stable radix sort, voxel representatives, ordered lists */
+        k_voxel_frame<<<nB, VX_T, sizeof(VxSmem), st>>>(d, ctx->force_vbits);
+        mark(ctx, "k_voxel_frame");
+        ctx->launches += 1;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
@@ -414,7 +370,7 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     sp_ctx *ctx = new sp_ctx();
     ctx->device = device; ctx->W = width; ctx->H = height; ctx->N = width * height; ctx->B = max_batch;
     { const char *t = getenv("SP_TRACE"); ctx->trace = t && *t && *t != '0'; }
-    { const char *t = getenv("SP_KEY64"); ctx->force_key64 = t && *t && *t != '0'; }
+    { const char *t = getenv("SP_VBITS"); ctx->force_vbits = t && *t ? std::max(0, std::min(32, atoi(t))) : 0; }
     { const char *t = getenv("SP_NO_TWIN"); ctx->no_twin = t && *t && *t != '0'; }
     { const char *t = getenv("SP_LANES"); if (t && *t) ctx->want_lanes = std::max(1, std::min(4, atoi(t))); if (ctx->want_lanes < 2) ctx->no_twin = true; }
     memset(&ctx->d, 0, sizeof(ctx->d));
@@ -441,9 +397,9 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     if (staging) { DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9); }
     DA(d.xyzw, BN); DA(d.nrm, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
-    DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.foff, B + 2);
+    DA(d.vcnt, B * d.nblk);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
-    DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
+    DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
     DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
     DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
     DA(d.n_clusters, S); DA(d.n_cand, S);
@@ -478,6 +434,8 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     if ((e = cudaMallocHost((void **)&ctx->h_results, sizeof(sp_frame_result) * B * 2)) != cudaSuccess) return fail("cudaMallocHost", e);
     for (int i = 0; i < 2; ++i) if ((e = cudaEventCreateWithFlags(&ctx->ev_res[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
+        return fail("cudaFuncSetAttribute", e);
+    if ((e = cudaFuncSetAttribute(k_voxel_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VxSmem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
@@ -588,7 +546,7 @@ static sp_ctx *twin_of(sp_ctx *ctx, sp_ctx *after)
     if (after->twin) return after->twin;
     sp_ctx *t = nullptr;
     if (create_impl(&ctx->params, ctx->device, ctx->W, ctx->H, ctx->B, false, &t) != SP_OK) { ctx->no_twin = true; (void)cudaGetLastError(); return nullptr; }
-    t->owner = ctx; t->trace = false; t->force_key64 = ctx->force_key64;
+    t->owner = ctx; t->trace = false; t->force_vbits = ctx->force_vbits;
     after->twin = t;
     return t;
 }
@@ -940,18 +898,15 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         return SP_OK;
     }
     if (name == "voxel_key") {
-        std::vector<int> fo(2); CK(d2h(fo.data(), d.foff + f, 8));
-        const size_t M = (size_t)std::max(0, fo[1] - fo[0]);
-        std::vector<unsigned long long> k(M); std::vector<unsigned> v(M);
-        if (d.key32) {
-            std::vector<unsigned> k4(M);
-            CK(d2h(k4.data(), reinterpret_cast<unsigned *>(d.key_a) + fo[0], M * 4));
-            for (size_t i = 0; i < M; ++i) k[i] = k4[i] & (unsigned)((1ull << d.vbits) - 1ull);   /* vbits <= 32 */
-        } else CK(d2h(k.data(), d.key_a + fo[0], M * 8));
-        CK(d2h(v.data(), d.val_a + fo[0], M * 4));
+        /* voxel index per pixel, from the frame's sorted (voxel index, pixel) pairs */
+        SpFrameGrid g; CK(d2h(&g, d.grid + f, sizeof(g)));
+        const size_t M = g.status == 0 ? (size_t)std::max(0, counts[2]) : 0;
+        std::vector<unsigned> k(M), v(M);
+        CK(d2h(k.data(), reinterpret_cast<unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + f * N, M * 4));
+        CK(d2h(v.data(), (g.sorted_in_b ? d.val_b : d.val_a) + f * N, M * 4));
         out.resize(N * 4); uint32_t *o = (uint32_t *)out.data();
         for (size_t i = 0; i < N; ++i) o[i] = 0xFFFFFFFFu;
-        for (size_t i = 0; i < M; ++i) if (v[i] < N) o[v[i]] = (uint32_t)k[i];
+        for (size_t i = 0; i < M; ++i) if (v[i] < N) o[v[i]] = k[i];
         return SP_OK;
     }
     if (name == "voxel_idx" || name == "nonan_idx" || name == "noleg_idx" || name == "voxel_code") {

@@ -37,6 +37,7 @@ struct SpFrameGrid {           /* voxel grid of one frame, voxel_grid_indices.hp
     int mul[3];
     int status;                /* 0 ok, 1 = <100 points after crop, 2 = overflow guard */
     int cells;                 /* dx * dy * dz: every voxel index of the frame is below it */
+    int sorted_in_b;           /* which of the two (key, pixel) buffers holds the frame's sorted pairs (odd number of sort passes: b) */
 };
 
 struct SpSegPlane {            /* one plane out of RANSAC (slot order = cluster rank, then call order) */
@@ -81,18 +82,9 @@ struct SpDev {
     int *counts;               /* [B][SP_NCOUNT] */
     SpFrameGrid *grid;
     int *vcnt;                 /* [B][nblk] cropped pixels per 1024-pixel block (K1K2 counts them, the voxel stage compacts by them) */
-    int *voff;                 /* [B][nblk] exclusive scan of vcnt inside the frame */
-    int *foff;                 /* [B + 2] offset of each frame's cropped points in the compacted sort arrays; foff[B'] = total,
-                                  foff[B' + 1] = largest voxel grid (cells) among the chunk's frames */
     /* voxel */
-    unsigned long long *key_a, *key_b;   /* only the cropped points are sorted: compacted, frame after frame, pixel order inside */
+    unsigned long long *key_a, *key_b;   /* k_voxel_frame: as u32 [B][N], the frame's cropped points (voxel index, pixel) before / after a sort pass; the kNN grid build uses them as u64 */
     unsigned *val_a, *val_b;
-    int key32, vbits, fgroup;  /* per chunk (run_chunk): 32-bit sort keys ((frame % fgroup) << vbits | voxel index), sorted fgroup frames
-                                  at a time, whenever the chunk's largest grid leaves room for at least 32 frames beside the voxel bits;
-                                  else 64-bit keys (frame << 32 | voxel index) in one sort */
-    int *rep;                  /* [B][N] */
-    unsigned char *code;       /* [B][N] */
-    int *blk;                  /* [B][nblk][5] per-1024-block counts: head, nonan, noleg, H, V */
     int nblk;
     int *voxel_idx;            /* [B][N] */
     unsigned char *voxel_code; /* [B][N] */

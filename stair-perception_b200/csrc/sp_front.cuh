@@ -663,249 +663,6 @@ __global__ void k_init_frames(SpDev d, int nB)
     if (i < 2 * nB) { d.seg_n[i] = 0; d.n_clusters[i] = 0; d.n_cand[i] = 0; d.log_n[i] = 0; d.n_seg[i] = 0; d.n_merged[i] = 0; }
 }
 
-/* voxel grid of each frame: getMinMax3D result -> min_b, div_b, divb_mul (voxel_grid_indices.hpp:292-318)
- * plus the "<100 points" guard of process() (StairPerception.cpp:56). */
-__global__ void k_frame_grid(SpDev d, int nB)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nB) return;
-    SpFrameGrid g;
-    g.status = 0; g.cells = 0;
-    const int ncrop = d.counts[f * SP_NCOUNT + 2];
-    for (int k = 0; k < 3; ++k) { g.minb[k] = 0; g.mul[k] = 0; }
-    if (ncrop < 100) g.status = 1;
-    else {
-        const int *mm = d.mm + f * 8;
-        const float mnx = sp_ord2f(mm[0]), mny = sp_ord2f(mm[1]), mnz = sp_ord2f(mm[2]);
-        const float mxx = sp_ord2f(mm[3]), mxy = sp_ord2f(mm[4]), mxz = sp_ord2f(mm[5]);
-        const long long dx = (long long)((mxx - mnx) * d.c.ivx) + 1, dy = (long long)((mxy - mny) * d.c.ivy) + 1,
-                        dz = (long long)((mxz - mnz) * d.c.ivz) + 1;
-        if (dx * dy * dz > 2147483647LL) g.status = 2;
-        else {
-            g.minb[0] = (int)floorf(mnx * d.c.ivx); g.minb[1] = (int)floorf(mny * d.c.ivy); g.minb[2] = (int)floorf(mnz * d.c.ivz);
-            const int m0 = (int)floorf(mxx * d.c.ivx), m1 = (int)floorf(mxy * d.c.ivy);
-            const int d0 = m0 - g.minb[0] + 1, d1 = m1 - g.minb[1] + 1;
-            g.mul[0] = 1; g.mul[1] = d0; g.mul[2] = d0 * d1;
-            /* bound of the voxel indices k_voxel_key forms (floor differences, one more than dx, dy, dz at most); a product past
-             * int range means wrapped indices that need all 32 bits */
-            const long long d2 = (long long)((int)floorf(mxz * d.c.ivz) - g.minb[2] + 1);
-            const long long cells = (long long)d0 * d1 * d2;
-            g.cells = cells > 2147483647LL ? -1 : (int)cells;
-        }
-    }
-    d.grid[f] = g;
-    d.counts[f * SP_NCOUNT + 0] = g.status;
-}
-
-/* Only the cropped points go through the sort.  K1K2 left the number of cropped pixels per 1024-pixel block in vcnt; this
- * kernel turns them into offsets: inside the frame (one CTA per frame) ... */
-__global__ void __launch_bounds__(256) k_voxel_offsets(SpDev d)
-{
-    __shared__ int ws[8];
-    __shared__ int carry;
-    const int f = blockIdx.x, nblk = d.nblk;
-    const bool live = d.grid[f].status == 0;
-    const int *cnt = d.vcnt + (size_t)f * nblk;
-    int *off = d.voff + (size_t)f * nblk;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int b0 = 0; b0 < nblk; b0 += 256) {
-        const int b = b0 + threadIdx.x;
-        const int v = (live && b < nblk) ? cnt[b] : 0;
-        int inc = v;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) ws[wid] = inc;
-        __syncthreads();
-        int add = carry;
-        for (int w = 0; w < wid; ++w) add += ws[w];
-        if (b < nblk) off[b] = add + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 255) carry = add + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) d.foff[f + 1] = carry;          /* frame total, scanned by k_frame_offsets */
-}
-
-/* ... and across the frames of the chunk (one CTA); foff[nB] = number of elements to sort */
-__global__ void __launch_bounds__(1024) k_frame_offsets(SpDev d, int nB)
-{
-    __shared__ int ws[32];
-    __shared__ int carry, cmax;
-    if (threadIdx.x == 0) { carry = 0; cmax = 0; d.foff[0] = 0; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int f0 = 0; f0 < nB; f0 += 1024) {
-        const int f = f0 + threadIdx.x;
-        const int v = f < nB ? d.foff[f + 1] : 0;
-        if (f < nB) { const int c = d.grid[f].cells; atomicMax(&cmax, c < 0 ? 0x7fffffff : c); }
-        int inc = v;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) ws[wid] = inc;
-        __syncthreads();
-        int add = carry;
-        for (int w = 0; w < wid; ++w) add += ws[w];
-        __syncthreads();
-        if (f < nB) d.foff[f + 1] = add + inc;
-        if (threadIdx.x == 1023) carry = add + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) d.foff[nB + 1] = cmax;
-}
-
-/* voxel key per cropped point (voxel_grid_indices.hpp:378-394), written compacted in pixel order: one CTA per 1024 pixels */
-__global__ void __launch_bounds__(256) k_voxel_key(SpDev d)
-{
-    __shared__ int wsum[33];
-    const int f = blockIdx.y, N = d.N;
-    const SpFrameGrid g = d.grid[f];
-    if (g.status != 0) return;
-    int pos = d.foff[f] + d.voff[(size_t)f * d.nblk + blockIdx.x];
-    for (int q = 0; q < 4; ++q) {
-        const int i = blockIdx.x * 1024 + q * 256 + threadIdx.x;
-        bool ok = false; unsigned key = 0;
-        if (i < N) {
-            const size_t gi = (size_t)f * N + i;
-            const float4 pw = d.xyzw[gi];
-            const float px = pw.x, py = pw.y, pz = pw.z;
-            if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
-                const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
-                const int b = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
-                const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
-                key = (unsigned)(a * g.mul[0] + b * g.mul[1] + c * g.mul[2]);
-                ok = true;
-            }
-        }
-        int tot;
-        const int r = sp_block_scan_flag(ok, wsum, &tot);
-        if (ok) {
-            if (d.key32) reinterpret_cast<unsigned *>(d.key_a)[pos + r] = (d.fgroup > 1 ? ((unsigned)(f & (d.fgroup - 1)) << d.vbits) : 0u) | key;
-            else d.key_a[pos + r] = ((unsigned long long)(unsigned)f << 32) | key;
-            d.val_a[pos + r] = (unsigned)i;
-        }
-        pos += tot;
-    }
-}
-
-/* After the stable radix sort: one thread per sorted position.  The thread at the head of a run of equal keys
- * walks the run: sequential float centroid (pcl::CentroidPoint), first strictly-nearest point
- * (voxel_grid_indices.hpp:489-513), then the three point filters a6-a8 (StairPerception.cpp:598-713) on the
- * representative.  Per-1024-block class counts feed the list scatter. */
-__global__ void __launch_bounds__(256) k_voxel_pick(SpDev d)
-{
-    __shared__ int cnt[5];
-    const int f = blockIdx.y, N = d.N;
-    const size_t base = (size_t)f * N;
-    if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const int M = d.foff[f + 1] - d.foff[f];                       /* this frame's cropped points, sorted by voxel */
-    const bool k32 = d.key32 != 0;
-    const unsigned long long *keys64 = d.key_b + d.foff[f];
-    const unsigned *keys32 = reinterpret_cast<const unsigned *>(d.key_b) + d.foff[f];
-    auto key_at = [&](int t) -> unsigned long long { return k32 ? (unsigned long long)keys32[t] : keys64[t]; };
-    const unsigned *vals = d.val_b + d.foff[f];
-    const float4 *P = d.xyzw + base;
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-    for (int q = 0; q < 4; ++q) {
-        const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
-        if (j >= M) break;
-        unsigned char code = 0; int rep = -1;
-        const unsigned long long key = key_at(j);
-        if (j == 0 || key_at(j - 1) != key) {
-            float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-            for (int t = j; t < M && key_at(t) == key; ++t) { const float4 pw = P[vals[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
-            const float fn = (float)n;
-            const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
-            float best = FLT_MAX;
-            for (int t = j; t < j + n; ++t) {
-                const unsigned p = vals[t];
-                const float4 pw = P[p];
-                const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
-                const float dis = dx * dx + dy * dy + dz * dz;
-                if (best > dis) { best = dis; rep = (int)p; }
-            }
-            code = SPC_HEAD; ++c0;
-            const float4 nw = d.nrm[base + rep];
-            const float nx = nw.x, ny = nw.y, nz = nw.z;
-            if (sp_finite3(nx, ny, nz)) {
-                code |= SPC_NONAN; ++c1;
-                const float4 pw = P[rep];
-                const float px = pw.x, py = pw.y, pz = pw.z;
-                if (px * px + py * py + pz * pz > d.c.noleg_th2) {
-                    code |= SPC_NOLEG; ++c2;
-                    if (nx >= d.c.h_ge || nx <= d.c.h_le) { code |= SPC_H; ++c3; }
-                    else if (nx >= d.c.v_lo && nx <= d.c.v_hi) { code |= SPC_V; ++c4; }
-                }
-            }
-        }
-        d.rep[base + j] = rep; d.code[base + j] = code;                       /* positions past M are never read */
-    }
-    c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
-    c3 = __reduce_add_sync(0xffffffffu, c3); c4 = __reduce_add_sync(0xffffffffu, c4);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); atomicAdd(&cnt[2], c2); atomicAdd(&cnt[3], c3); atomicAdd(&cnt[4], c4); }
-    __syncthreads();
-    if (threadIdx.x < 5) d.blk[((size_t)f * d.nblk + blockIdx.x) * 5 + threadIdx.x] = cnt[threadIdx.x];
-}
-
-/* exclusive scan of the per-block counts of one frame (one CTA per frame) + frame totals */
-__global__ void __launch_bounds__(256) k_scan_blocks(SpDev d)
-{
-    __shared__ int carry[5];
-    __shared__ int ws[5][8];
-    const int f = blockIdx.x, nblk = d.nblk;
-    int *blk = d.blk + (size_t)f * nblk * 5;
-    if (threadIdx.x < 5) carry[threadIdx.x] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int b0 = 0; b0 < nblk; b0 += 256) {
-        const int b = b0 + threadIdx.x;
-        int v[5], inc[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { v[k] = b < nblk ? blk[b * 5 + k] : 0; inc[k] = v[k]; }
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc[k], o); if (lane >= o) inc[k] += t; }
-        if (lane == 31) { for (int k = 0; k < 5; ++k) ws[k][wid] = inc[k]; }
-        __syncthreads();
-        int add[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { int a = carry[k]; for (int w = 0; w < wid; ++w) a += ws[k][w]; add[k] = a; }
-        if (b < nblk) { for (int k = 0; k < 5; ++k) blk[b * 5 + k] = add[k] + inc[k] - v[k]; }
-        __syncthreads();
-        if (threadIdx.x == 255) { for (int k = 0; k < 5; ++k) carry[k] = add[k] + inc[k]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        int *c = d.counts + f * SP_NCOUNT;
-        c[3] = carry[0]; c[4] = carry[1]; c[5] = carry[2]; c[6] = carry[3]; c[7] = carry[4];
-        d.seg_n[2 * f] = carry[3]; d.seg_n[2 * f + 1] = carry[4];
-    }
-}
-
-/* ordered scatter: voxel representative list (+ class code) and the horizontal / vertical point sets */
-__global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
-{
-    __shared__ int wsum[33];
-    const int f = blockIdx.y, N = d.N;
-    const size_t base = (size_t)f * N;
-    const int M = d.foff[f + 1] - d.foff[f];                              /* sorted positions of this frame */
-    if (blockIdx.x * 1024 >= M) return;
-    const int *blk = d.blk + ((size_t)f * d.nblk + blockIdx.x) * 5;
-    int b_head = blk[0], b_h = blk[3], b_v = blk[4];
-    for (int q = 0; q < 4; ++q) {
-        const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
-        const unsigned char code = j < M ? d.code[base + j] : 0;
-        const int rep = j < M ? d.rep[base + j] : -1;
-        int tot;
-        const int pk = sp_block_scan_flags3((code & SPC_HEAD) != 0, (code & SPC_H) != 0, (code & SPC_V) != 0, wsum, &tot);
-        const int ph = pk & 1023, pH = (pk >> 10) & 1023, pV = pk >> 20;
-        if (code & SPC_HEAD) { d.voxel_idx[base + b_head + ph] = rep; d.voxel_code[base + b_head + ph] = code; }
-        if (code & SPC_H) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f) * N + b_h + pH] = pw; }
-        if (code & SPC_V) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f + 1) * N + b_v + pV] = pw; }
-        b_head += tot & 1023; b_h += (tot >> 10) & 1023; b_v += tot >> 20;
-    }
-}
-
 /* ==================================================================================================== */
 /* Depth-image ingest: K2G::updateCloud (/root/reference/modules/k2g/k2g.cpp:231-308) with the pinhole maps of
  * K2G::prepareMake3D (:506-520), on the device: (undistorted depth in mm, registered colour) -> the 16-byte cloud records

@@ -364,20 +364,23 @@ def test_mixed_batch_with_empty_and_sparse_frames(sp, orc, synth):
     ctx.close()
 
 
-def test_voxel_sort_64bit_key_path(sp, orc, synth, monkeypatch):
-    """The voxel sort normally runs on 32-bit keys ((frame in group) << voxel bits | voxel index); grids too large for that
-    take 64-bit keys.  SP_KEY64=1 forces the wide path on an ordinary batch: same bits out."""
-    monkeypatch.setenv("SP_KEY64", "1")
-    ctx = sp.Context(device=0, width=512, height=424, max_batch=3)
-    monkeypatch.delenv("SP_KEY64")
+def test_voxel_sort_four_pass_path(sp, orc, synth, monkeypatch):
+    """The per-frame voxel sort takes ceil(bits of the voxel grid / 9) stable passes: three for the usual grids, four when the
+    grid (or wrapped voxel indices) needs more than 27 bits.  SP_VBITS=32 forces the four-pass path on an ordinary batch, and
+    SP_VBITS=10 cannot shrink it below what the grid needs: same bits out.  (An even pass count also leaves the sorted pairs in
+    the other buffer, which the voxel_key tap must follow.)"""
     recs, Rs = zip(*[synth.make_frame(fid) for fid in (4, 6, 8)])
-    res = ctx.process_frames(np.stack(recs), np.stack(Rs))
-    for i in range(3):
-        o = orc.Oracle(sp.DEFAULT_PARAMS)
-        o.process(recs[i], 512, 424, Rs[i])
-        bad = compare_frame(ctx, i, res[i], o)
-        assert not bad, "frame %d\n" % i + "\n".join(bad[:20])
-    ctx.close()
+    for bits in ("32", "10"):
+        monkeypatch.setenv("SP_VBITS", bits)
+        ctx = sp.Context(device=0, width=512, height=424, max_batch=3)
+        monkeypatch.delenv("SP_VBITS")
+        res = ctx.process_frames(np.stack(recs), np.stack(Rs))
+        for i in range(3):
+            o = orc.Oracle(sp.DEFAULT_PARAMS)
+            o.process(recs[i], 512, 424, Rs[i])
+            bad = compare_frame(ctx, i, res[i], o)
+            assert not bad, "frame %d\n" % i + "\n".join(bad[:20])
+        ctx.close()
 
 
 def test_normals_without_the_exactness_guarantee(sp, orc, synth):
