@@ -398,7 +398,7 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     DA(d.xyzw, BN); DA(d.nrm, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
     DA(d.vcnt, B * d.nblk);
-    DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN); DA(d.val_b, BN);
+    DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN + 4 * B); DA(d.val_b, BN + 4 * B);      /* k_voxel_frame: slices of (N + 3) & ~3 u32 per frame */
     DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
     DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
     DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
@@ -902,8 +902,9 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         SpFrameGrid g; CK(d2h(&g, d.grid + f, sizeof(g)));
         const size_t M = g.status == 0 ? (size_t)std::max(0, counts[2]) : 0;
         std::vector<unsigned> k(M), v(M);
-        CK(d2h(k.data(), reinterpret_cast<unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + f * N, M * 4));
-        CK(d2h(v.data(), (g.sorted_in_b ? d.val_b : d.val_a) + f * N, M * 4));
+        const size_t Ns = (N + 3) & ~(size_t)3;
+        CK(d2h(k.data(), reinterpret_cast<unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + f * Ns, M * 4));
+        CK(d2h(v.data(), (g.sorted_in_b ? d.val_b : d.val_a) + f * Ns, M * 4));
         out.resize(N * 4); uint32_t *o = (uint32_t *)out.data();
         for (size_t i = 0; i < N; ++i) o[i] = 0xFFFFFFFFu;
         for (size_t i = 0; i < M; ++i) if (v[i] < N) o[v[i]] = k[i];

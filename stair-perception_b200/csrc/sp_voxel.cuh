@@ -21,6 +21,7 @@
  */
 #pragma once
 #include "sp_common.cuh"
+#include "sp_async.cuh"
 
 #define VX_T 512
 #define VX_NW (VX_T / 32)
@@ -29,19 +30,37 @@
 #define VX_RB 9
 #define VX_BINS (1 << VX_RB)
 #define VX_PE 4                          /* sorted positions per thread and tile of the run-head pass */
+#define VX_OV 64                         /* positions staged past the end of a tile: a run that starts in the tile usually ends there */
 static_assert(VX_T == VX_BINS, "one digit per thread in the bin scans");
 
-struct VxSmem {
+#define VX_KT (VX_T * 4)                  /* pixels per tile of the key pass */
+struct __align__(128) VxSmem {
+    /* staging, by phase (the phases never overlap): raw tiles arrive here by bulk async copies (TMA, completion on mbar) */
+    union {
+        float4 kg[2][VX_KT];                                            /* key pass: levelled points of a tile, double-buffered */
+        struct { unsigned k[2][VX_TILE], v[2][VX_TILE]; } so;           /* sort pass: (voxel index, pixel) of a tile, double-buffered */
+        struct {
+            float4 pt[VX_T * VX_PE + VX_OV];                            /* run pass: the tile's points {x, y, z, pixel} in sorted order */
+            unsigned pk[VX_T * VX_PE + VX_OV + 1];                      /*           their voxel indices; [0] = the key before the tile */
+            int heads[VX_T * VX_PE];                                    /*           run heads of the tile, in order */
+        } pi;
+    } u;
     unsigned wc[VX_NW][VX_BINS];         /* per-warp digit counters of a tile, then the warps' scatter offsets */
     unsigned hist[4][VX_BINS];           /* digit histograms of the (up to four) passes */
     unsigned binoff[VX_BINS];            /* running offset of every digit of the current pass */
-    int heads[VX_T * VX_PE];             /* run heads of a tile, in order */
     int wsum[VX_NW + 1];
     int wsum3[33];                       /* sp_block_scan_flags3 keeps its total in [32] */
     SpFrameGrid g;
     int vbits, npass;
-    int carry[6];                        /* voxels, non-NaN, no-leg, H, V so far; [5] = M */
+    unsigned long long mbar[2];
 };
+
+/* contiguous global -> shared bulk copy (TMA, SASS UBLKCP); bytes a multiple of 16, both ends 16-byte aligned */
+__device__ __forceinline__ void vx_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(st_sptr(dst)), "l"(src), "r"(bytes), "r"(st_sptr(bar)) : "memory");
+}
 
 __device__ __forceinline__ int vx_block_excl(int v, int *ws, int *total)       /* exclusive block scan of an int, VX_T threads */
 {
@@ -67,13 +86,19 @@ __device__ __forceinline__ int vx_block_excl(int v, int *ws, int *total)       /
 
 __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits)
 {
-    extern __shared__ __align__(16) unsigned char vx_raw[];
+    extern __shared__ __align__(128) unsigned char vx_raw[];
     VxSmem &s = *reinterpret_cast<VxSmem *>(vx_raw);
     const int f = blockIdx.x, N = d.N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const size_t base = (size_t)f * N;
+    const size_t sbase = (size_t)f * (size_t)((N + 3) & ~3);             /* the frame's slice of the sort arrays (16-byte aligned) */
     int *cnts = d.counts + f * SP_NCOUNT;
+    if (tid == 0) {
+        st_mbar_init(&s.mbar[0], 1); st_mbar_init(&s.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned ph = 0;                                                         /* bit b = parity the next wait on mbar[b] expects */
 
     /* ---- 1. the frame's grid (k_frame_grid of round 1) */
     if (tid == 0) {
@@ -109,7 +134,6 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
         s.g = g; s.vbits = vbits; s.npass = npass;
         d.grid[f] = g;
         cnts[0] = g.status;
-        for (int k = 0; k < 6; ++k) s.carry[k] = 0;
     }
     for (int k = tid; k < 4 * VX_BINS; k += VX_T) (&s.hist[0][0])[k] = 0u;
     __syncthreads();
@@ -119,56 +143,80 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
         return;
     }
     const int npass = s.npass;
-    unsigned *ka = reinterpret_cast<unsigned *>(d.key_a) + base, *kb = reinterpret_cast<unsigned *>(d.key_b) + base;
-    unsigned *va = d.val_a + base, *vb = d.val_b + base;
+    unsigned *ka = reinterpret_cast<unsigned *>(d.key_a) + sbase, *kb = reinterpret_cast<unsigned *>(d.key_b) + sbase;
+    unsigned *va = d.val_a + sbase, *vb = d.val_b + sbase;
     const float4 *P = d.xyzw + base;
 
-    /* ---- 2. voxel index per cropped point, compacted in pixel order (warp-striped tiles: position order = (warp, k, lane)) */
+    /* ---- 2. voxel index per cropped point, compacted in pixel order (warp-striped tiles: position order = (warp, k, lane)).
+     * The levelled points of tile i + 1 are in flight (bulk copy) while tile i is processed */
     int M = 0;
-    for (int t0 = 0; t0 < N; t0 += VX_TILE) {
-        const int cb = t0 + wid * (32 * VX_E);
-        unsigned key[VX_E];
-        unsigned okm = 0;
-        int rank[VX_E], cnt = 0;
+    {
+        const int nkt = (N + VX_KT - 1) / VX_KT;
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)min(VX_KT, N) * 16u;
+            st_mbar_expect(&s.mbar[0], bytes);
+            vx_bulk(&s.u.kg[0][0], P, bytes, &s.mbar[0]);
+        }
+        for (int it = 0; it < nkt; ++it) {
+            const int t0 = it * VX_KT, b = it & 1;
+            if (tid == 0 && it + 1 < nkt) {                                  /* buffer b ^ 1 was consumed before the last barrier */
+                const unsigned bytes = (unsigned)min(VX_KT, N - (t0 + VX_KT)) * 16u;
+                st_mbar_expect(&s.mbar[b ^ 1], bytes);
+                vx_bulk(&s.u.kg[b ^ 1][0], P + t0 + VX_KT, bytes, &s.mbar[b ^ 1]);
+            }
+            st_mbar_wait(&s.mbar[b], (ph >> b) & 1u); ph ^= 1u << b;
+            const int cl = wid * (32 * 4);
+            unsigned key[4];
+            unsigned okm = 0;
+            int rank[4], cnt = 0;
 #pragma unroll
-        for (int k = 0; k < VX_E; ++k) {
-            const int i = cb + k * 32 + lane;
-            bool ok = false; unsigned ky = 0;
-            if (i < N) {
-                const float4 pw = P[i];
-                const float px = pw.x, py = pw.y, pz = pw.z;
-                if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
-                    const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
-                    const int b = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
-                    const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
-                    ky = (unsigned)(a * g.mul[0] + b * g.mul[1] + c * g.mul[2]);
-                    ok = true;
+            for (int k = 0; k < 4; ++k) {
+                const int q = cl + k * 32 + lane, i = t0 + q;
+                bool ok = false; unsigned ky = 0;
+                if (i < N) {
+                    const float4 pw = s.u.kg[b][q];
+                    const float px = pw.x, py = pw.y, pz = pw.z;
+                    if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
+                        const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
+                        const int bq = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
+                        const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
+                        ky = (unsigned)(a * g.mul[0] + bq * g.mul[1] + c * g.mul[2]);
+                        ok = true;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                key[k] = ky; rank[k] = cnt + __popc(bal & lt); cnt += __popc(bal);
+                if (ok) okm |= 1u << k;
+            }
+            int tot;
+            const int wbase = vx_block_excl(lane == 0 ? cnt : 0, s.wsum, &tot);   /* lane 0 of each warp carries the warp's count */
+            const int wb = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (okm & (1u << k)) {
+                    const int pos = M + wb + rank[k];
+                    ka[pos] = key[k]; va[pos] = (unsigned)(t0 + cl + k * 32 + lane);
+                    for (int p = 0; p < npass; ++p) atomicAdd(&s.hist[p][(key[k] >> (p * VX_RB)) & (VX_BINS - 1)], 1u);
                 }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            key[k] = ky; rank[k] = cnt + __popc(bal & lt); cnt += __popc(bal);
-            if (ok) okm |= 1u << k;
+            M += tot;
         }
-        int tot;
-        const int wbase = vx_block_excl(lane == 0 ? cnt : 0, s.wsum, &tot);       /* lane 0 of each warp carries the warp's count */
-        const int wb = __shfl_sync(0xffffffffu, wbase, 0);
-#pragma unroll
-        for (int k = 0; k < VX_E; ++k) {
-            if (okm & (1u << k)) {
-                const int pos = M + wb + rank[k];
-                ka[pos] = key[k]; va[pos] = (unsigned)(cb + k * 32 + lane);
-                for (int p = 0; p < npass; ++p) atomicAdd(&s.hist[p][(key[k] >> (p * VX_RB)) & (VX_BINS - 1)], 1u);
-            }
-        }
-        M += tot;
     }
+    asm volatile("fence.proxy.async;" ::: "memory");                        /* the pairs written above are read by bulk copies below */
     __syncthreads();
 
-    /* ---- 3. stable LSD radix sort */
+    /* ---- 3. stable LSD radix sort; tile i + 1 of the source is in flight while tile i is ranked and scattered */
     for (int p = 0; p < npass; ++p) {
         const unsigned *sk = (p & 1) ? kb : ka, *sv = (p & 1) ? vb : va;
         unsigned *dk = (p & 1) ? ka : kb, *dv = (p & 1) ? va : vb;
         const int shift = p * VX_RB;
+        const int nt = (M + VX_TILE - 1) / VX_TILE;
+        if (tid == 0) {
+            const unsigned bytes = ((unsigned)min(VX_TILE, M) * 4u + 15u) & ~15u;
+            st_mbar_expect(&s.mbar[0], 2 * bytes);
+            vx_bulk(&s.u.so.k[0][0], sk, bytes, &s.mbar[0]);
+            vx_bulk(&s.u.so.v[0][0], sv, bytes, &s.mbar[0]);
+        }
         {
             int tot;
             const int e = vx_block_excl((int)s.hist[p][tid], s.wsum, &tot);       /* VX_T == VX_BINS: one digit per thread */
@@ -176,14 +224,19 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
         }
         for (int k = lane; k < VX_BINS; k += 32) s.wc[wid][k] = 0u;
         __syncthreads();
-        for (int t0 = 0; t0 < M; t0 += VX_TILE) {
-            const int cb = t0 + wid * (32 * VX_E);
+        for (int it = 0; it < nt; ++it) {
+            const int t0 = it * VX_TILE, b = it & 1;
+            if (tid == 0 && it + 1 < nt) {
+                const unsigned bytes = ((unsigned)min(VX_TILE, M - (t0 + VX_TILE)) * 4u + 15u) & ~15u;
+                st_mbar_expect(&s.mbar[b ^ 1], 2 * bytes);
+                vx_bulk(&s.u.so.k[b ^ 1][0], sk + t0 + VX_TILE, bytes, &s.mbar[b ^ 1]);
+                vx_bulk(&s.u.so.v[b ^ 1][0], sv + t0 + VX_TILE, bytes, &s.mbar[b ^ 1]);
+            }
+            st_mbar_wait(&s.mbar[b], (ph >> b) & 1u); ph ^= 1u << b;
+            const int cl = wid * (32 * VX_E), cb = t0 + cl;
             unsigned key[VX_E], val[VX_E], rank[VX_E];
 #pragma unroll
-            for (int k = 0; k < VX_E; ++k) {
-                const int j = cb + k * 32 + lane;
-                key[k] = j < M ? sk[j] : 0u; val[k] = j < M ? sv[j] : 0u;
-            }
+            for (int k = 0; k < VX_E; ++k) { key[k] = s.u.so.k[b][cl + k * 32 + lane]; val[k] = s.u.so.v[b][cl + k * 32 + lane]; }
 #pragma unroll
             for (int k = 0; k < VX_E; ++k) {
                 const int j = cb + k * 32 + lane;
@@ -216,6 +269,7 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
             __syncwarp();
             for (int k = lane; k < VX_BINS; k += 32) s.wc[wid][k] = 0u;      /* the warp's own row, for the next tile */
         }
+        asm volatile("fence.proxy.async;" ::: "memory");                    /* the next pass reads what this one wrote by bulk copies */
         __syncthreads();
     }
 
@@ -224,19 +278,34 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
     const size_t sH = (size_t)(2 * f) * N, sV = (size_t)(2 * f + 1) * N;
     int nvox = 0, nnonan = 0, nnoleg = 0, nH = 0, nV = 0;                    /* CTA-uniform running totals */
     for (int t0 = 0; t0 < M; t0 += VX_T * VX_PE) {
+        /* stage the tile: one parallel gather per sorted position (the run walks below then read shared memory, not a chain of
+         * dependent global loads) */
+        const int nst = min(M - t0, VX_T * VX_PE + VX_OV);
+        {
+            unsigned vv[VX_PE + 1], kq[VX_PE + 1];
+#pragma unroll
+            for (int k = 0; k <= VX_PE; ++k) { const int q = tid + k * VX_T; vv[k] = 0u; kq[k] = 0u; if (q < nst) { vv[k] = V[t0 + q]; kq[k] = K[t0 + q]; } }
+#pragma unroll
+            for (int k = 0; k <= VX_PE; ++k) {
+                const int q = tid + k * VX_T;
+                if (q < nst) { float4 pw = P[vv[k]]; pw.w = __uint_as_float(vv[k]); s.u.pi.pt[q] = pw; s.u.pi.pk[q + 1] = kq[k]; }
+            }
+            if (tid == 0) s.u.pi.pk[0] = t0 > 0 ? K[t0 - 1] : 0u;
+        }
+        __syncthreads();
         /* heads of this tile, in order */
         int hcnt = 0;
         bool hd[VX_PE];
 #pragma unroll
         for (int k = 0; k < VX_PE; ++k) {
-            const int j = t0 + tid * VX_PE + k;
-            hd[k] = j < M && (j == 0 || K[j - 1] != K[j]);
+            const int q = tid * VX_PE + k, j = t0 + q;
+            hd[k] = j < M && (j == 0 || s.u.pi.pk[q] != s.u.pi.pk[q + 1]);
             hcnt += hd[k] ? 1 : 0;
         }
         int nh;
         int hp = vx_block_excl(hcnt, s.wsum, &nh);
 #pragma unroll
-        for (int k = 0; k < VX_PE; ++k) if (hd[k]) s.heads[hp++] = t0 + tid * VX_PE + k;
+        for (int k = 0; k < VX_PE; ++k) if (hd[k]) s.u.pi.heads[hp++] = tid * VX_PE + k;
         __syncthreads();
         for (int u0 = 0; u0 < nh; u0 += VX_T) {
             const int u = u0 + tid;
@@ -244,20 +313,24 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
             int rep = -1; unsigned char code = 0;
             float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
             if (u < nh) {
-                const int j = s.heads[u];
-                const unsigned key = K[j];
+                const int q0 = s.u.pi.heads[u];
+                const unsigned key = s.u.pi.pk[q0 + 1];
                 float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-                for (int t = j; t < M && K[t] == key; ++t) { const float4 pw = P[V[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
+                int q = q0;
+                for (; q < nst && s.u.pi.pk[q + 1] == key; ++q) { const float4 pw = s.u.pi.pt[q]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
+                if (q == nst) for (int t = t0 + q; t < M && K[t] == key; ++t) { const float4 pw = P[V[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }   /* a run past the staged part */
                 const float fn = (float)n;
                 const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
                 float best = FLT_MAX;
-                for (int t = j; t < j + n; ++t) {
-                    const unsigned p = V[t];
-                    const float4 pw = P[p];
+                for (int e = 0; e < n; ++e) {
+                    float4 pw;
+                    if (q0 + e < nst) pw = s.u.pi.pt[q0 + e];
+                    else { const unsigned p = V[t0 + q0 + e]; pw = P[p]; pw.w = __uint_as_float(p); }
                     const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
                     const float dis = dx * dx + dy * dy + dz * dz;
-                    if (best > dis) { best = dis; rep = (int)p; rp = pw; }
+                    if (best > dis) { best = dis; rp = pw; }
                 }
+                rep = (int)__float_as_uint(rp.w);
                 code = SPC_HEAD;
                 const float4 nw = d.nrm[base + rep];
                 const float nx = nw.x, ny = nw.y, nz = nw.z;
@@ -272,14 +345,14 @@ __global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits
                 d.voxel_idx[base + nvox + u] = rep; d.voxel_code[base + nvox + u] = code;
             }
             int tot3;
-            const int pk = sp_block_scan_flags3(fH, fV, fNN, s.wsum3, &tot3);  /* 10-bit fields: VX_T = 512 < 1023 */
+            const int pk3 = sp_block_scan_flags3(fH, fV, fNN, s.wsum3, &tot3);  /* 10-bit fields: VX_T = 512 < 1023 */
             const int cNL = __syncthreads_count(fNL);
-            if (fH) { rp.w = __int_as_float(rep); d.pts[sH + nH + (pk & 1023)] = rp; }
-            if (fV) { rp.w = __int_as_float(rep); d.pts[sV + nV + ((pk >> 10) & 1023)] = rp; }
+            if (fH) d.pts[sH + nH + (pk3 & 1023)] = rp;                          /* {x, y, z, pixel} */
+            if (fV) d.pts[sV + nV + ((pk3 >> 10) & 1023)] = rp;
             nH += tot3 & 1023; nV += (tot3 >> 10) & 1023; nnonan += tot3 >> 20; nnoleg += cNL;
         }
         nvox += nh;
-        __syncthreads();                                                     /* heads[] is rewritten by the next tile */
+        __syncthreads();                                                     /* heads[] and the staged tile are rewritten by the next tile */
     }
     if (tid == 0) {
         cnts[3] = nvox; cnts[4] = nnonan; cnts[5] = nnoleg; cnts[6] = nH; cnts[7] = nV;
