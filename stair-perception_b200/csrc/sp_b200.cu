@@ -271,10 +271,25 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     CK(cudaEventRecord(ctx->ev[1], st));
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
     if (want_voxel) {
-        /* the whole voxel stage of a frame in one CTA: grid, keys, stable radix sort, voxel representatives, ordered lists */
-        k_voxel_frame<<<nB, VX_T, sizeof(VxSmem), st>>>(d, ctx->force_vbits);
-        mark(ctx, "k_voxel_frame");
-        ctx->launches += 1;
+        /* no host round trip: the per-frame sizes and pass counts stay on the device (SpFrameGrid) */
+        k_vx_grid<<<(nB + 127) / 128, 128, 0, st>>>(d, nB, ctx->force_vbits);
+        k_vx_offsets<<<nB, 256, 0, st>>>(d);
+        mark(ctx, "k_vx_grid+offsets");
+        k_vx_key<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        mark(ctx, "k_vx_key");
+        for (int p = 0; p < VX_MAXPASS; ++p) {                              /* a frame whose grid needs fewer passes skips the rest */
+            k_vx_hist<<<dim3(d.ntile, nB), VX_T, 0, st>>>(d, p);
+            k_vx_scan<<<nB, VX_T, 0, st>>>(d, p);
+            k_vx_scatter<<<dim3(d.ntile, nB), VX_T, 0, st>>>(d, p);
+        }
+        mark(ctx, "radix_sort");
+        k_vx_pick<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        mark(ctx, "k_vx_pick");
+        k_scan_blocks<<<nB, 256, 0, st>>>(d);
+        mark(ctx, "k_scan_blocks");
+        k_scatter_lists<<<dim3(d.nblk, nB), 256, 0, st>>>(d);
+        mark(ctx, "k_scatter_lists");
+        ctx->launches += 6 + 3 * VX_MAXPASS;
     }
     CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
@@ -397,9 +412,10 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     if (staging) { DA(ctx->d_in[0], BN); DA(ctx->d_in[1], BN); DA(ctx->d_R[0], B * 9); DA(ctx->d_R[1], B * 9); }
     DA(d.xyzw, BN); DA(d.nrm, BN);
     DA(d.mm, B * 8); DA(d.counts, B * SP_NCOUNT); DA(d.grid, B); DA(d.flags, B);
-    DA(d.vcnt, B * d.nblk);
+    d.ntile = (int)(((N + 3) / 4 * 4 + VX_TILE - 1) / VX_TILE);
+    DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.vth, B * d.ntile * VX_BINS);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN + 4 * B); DA(d.val_b, BN + 4 * B);      /* k_voxel_frame: slices of (N + 3) & ~3 u32 per frame */
-    DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
+    DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
     DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
     DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
     DA(d.n_clusters, S); DA(d.n_cand, S);
@@ -434,8 +450,6 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     if ((e = cudaMallocHost((void **)&ctx->h_results, sizeof(sp_frame_result) * B * 2)) != cudaSuccess) return fail("cudaMallocHost", e);
     for (int i = 0; i < 2; ++i) if ((e = cudaEventCreateWithFlags(&ctx->ev_res[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
-        return fail("cudaFuncSetAttribute", e);
-    if ((e = cudaFuncSetAttribute(k_voxel_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VxSmem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
     if ((e = cudaFuncSetAttribute(k_ingest_normals_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem))) != cudaSuccess)
         return fail("cudaFuncSetAttribute", e);
@@ -900,7 +914,7 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
     if (name == "voxel_key") {
         /* voxel index per pixel, from the frame's sorted (voxel index, pixel) pairs */
         SpFrameGrid g; CK(d2h(&g, d.grid + f, sizeof(g)));
-        const size_t M = g.status == 0 ? (size_t)std::max(0, counts[2]) : 0;
+        const size_t M = (size_t)std::max(0, g.M);
         std::vector<unsigned> k(M), v(M);
         const size_t Ns = (N + 3) & ~(size_t)3;
         CK(d2h(k.data(), reinterpret_cast<unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + f * Ns, M * 4));

@@ -38,6 +38,8 @@ struct SpFrameGrid {           /* voxel grid of one frame, voxel_grid_indices.hp
     int status;                /* 0 ok, 1 = <100 points after crop, 2 = overflow guard */
     int cells;                 /* dx * dy * dz: every voxel index of the frame is below it */
     int sorted_in_b;           /* which of the two (key, pixel) buffers holds the frame's sorted pairs (odd number of sort passes: b) */
+    int npass;                 /* 9-bit radix passes the frame's voxel indices need (0 when process() stops before the voxel filter) */
+    int M;                     /* cropped points of the frame = pairs to sort (0 when process() stops before the voxel filter) */
 };
 
 struct SpSegPlane {            /* one plane out of RANSAC (slot order = cluster rank, then call order) */
@@ -82,8 +84,14 @@ struct SpDev {
     int *counts;               /* [B][SP_NCOUNT] */
     SpFrameGrid *grid;
     int *vcnt;                 /* [B][nblk] cropped pixels per 1024-pixel block (K1K2 counts them, the voxel stage compacts by them) */
+    int *voff;                 /* [B][nblk] exclusive scan of vcnt inside the frame */
+    unsigned *vth;             /* [B][ntile][512] sort: per (tile, digit) counts, then first destinations */
+    int ntile;                 /* sort tiles per frame slice */
+    int *rep;                  /* [B][N] per sorted position: the voxel's representative pixel (run heads) */
+    unsigned char *code;       /* [B][N] per sorted position: class bits (0 = not a run head) */
+    int *blk;                  /* [B][nblk][5] per-1024-block counts: head, nonan, noleg, H, V */
     /* voxel */
-    unsigned long long *key_a, *key_b;   /* k_voxel_frame: as u32 [B][N], the frame's cropped points (voxel index, pixel) before / after a sort pass; the kNN grid build uses them as u64 */
+    unsigned long long *key_a, *key_b;   /* voxel stage: as u32, a slice of (N + 3) & ~3 per frame: the frame's cropped points (voxel index, pixel) before / after a sort pass; the kNN grid build uses them as u64 */
     unsigned *val_a, *val_b;
     int nblk;
     int *voxel_idx;            /* [B][N] */

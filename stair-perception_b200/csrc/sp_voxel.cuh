@@ -1,361 +1,345 @@
 /*
- * sp_voxel.cuh -- the voxel stage of one frame in ONE kernel, one CTA per frame, no host round trip:
+ * sp_voxel.cuh -- the voxel stage: voxelGridCloudANDNormal (StairPerception.cpp:489-517) -> pcl::VoxelGridIndices::applyFilterIndices
+ * (/root/reference/modules/stairperception/voxel_grid_indices.hpp:277-517), followed by removeNANNormalPoints (:598-616),
+ * removeClosetPoints (:619-639) and extractPerpendicularPlanePoints (:670-713).
  *
- *   voxelGridCloudANDNormal (StairPerception.cpp:489-517) -> pcl::VoxelGridIndices::applyFilterIndices
- *   (/root/reference/modules/stairperception/voxel_grid_indices.hpp:277-517) followed by removeNANNormalPoints (:598-616),
- *   removeClosetPoints (:619-639) and extractPerpendicularPlanePoints (:670-713).
+ * Every frame owns a slice of the (voxel index, pixel) sort arrays and everything the host used to read back (how many
+ * cropped points a frame has, how many bits its voxel grid needs, which buffer ends up holding the sorted pairs) stays on the
+ * device in SpFrameGrid: the stage has no host round trip and can be captured in a CUDA graph.
  *
- *   1. grid of the frame from the crop box K1K2 left in d.mm (voxel_grid_indices.hpp:292-318) and the "< 100 points" guard
- *   2. voxel index per cropped point (:378-394), written compacted in pixel order (ordered block compaction), together with the
- *      digit histograms of every sort pass
- *   3. stable LSD radix sort of (voxel index, pixel) on 9-bit digits: ceil(bits of the grid / 9) passes (3 for the usual 2^26-cell
- *      grids), each a stable multi-split of 4096-element tiles: warp-striped keys, __match_any_sync ranks, per-warp digit counters
- *      in shared memory, one prefix over the warps per digit.  Stable = ascending pixel index inside a voxel: the oracle's
- *      documented tie rule for the reference's std::sort (:399)
- *   4. run heads of the sorted keys = voxels (:411-422).  Heads are compacted per tile so that every lane walks a run: sequential
- *      float centroid, first strictly-nearest point (:489-513), the three point filters on the representative.  The voxel list
- *      and the horizontal / vertical point sets come out in voxel order by block scans: no separate scatter pass
- *
- * Replaces k_frame_grid, k_voxel_offsets, k_frame_offsets, the host read of the offsets, k_voxel_key, cub::DeviceRadixSort,
- * k_voxel_pick, k_scan_blocks and k_scatter_lists of round 1.
+ *   k_vx_grid      grid of each frame from the crop box K1K2 left in d.mm (:292-318), the "< 100 points" guard, sort passes
+ *   k_vx_offsets   K1K2's cropped pixels per 1024-pixel block -> offsets inside the frame's slice
+ *   k_vx_key       voxel index per cropped point (:378-394), compacted in pixel order
+ *   k_vx_hist / k_vx_scan / k_vx_scatter, once per pass
+ *                  stable LSD radix sort on 9-bit digits, hand-written: tiles of 4096 pairs, (tile, digit) counts -> offsets by one
+ *                  CTA per frame, then every tile ranks its keys (warp-striped, __match_any_sync groups, per-warp digit counters
+ *                  in shared memory, one prefix over the warps per digit) and scatters.  A frame takes ceil(bits of its grid / 9)
+ *                  passes: three for the usual 2^26-cell grids; the launches of a pass a frame does not need return at once.
+ *                  Stable = ascending pixel index inside a voxel: the oracle's documented tie rule for the reference's std::sort (:399)
+ *   k_vx_pick      runs of equal keys = voxels (:411-422): the head of a run walks it: sequential float centroid, first
+ *                  strictly-nearest point (:489-513), the three point filters on the representative
+ *   k_scan_blocks, k_scatter_lists   ordered voxel list and horizontal / vertical point sets
+ * One CTA per frame for the whole stage (tried in this round) serialises a frame: 2.9 ms per 256 frames and twice
+ * the single-frame latency; tiles keep every SM busy at any batch size.
  */
 #pragma once
 #include "sp_common.cuh"
-#include "sp_async.cuh"
 
 #define VX_T 512
 #define VX_NW (VX_T / 32)
-#define VX_E 8                           /* keys per thread and tile */
+#define VX_E 8                           /* keys per thread of a sort tile */
 #define VX_TILE (VX_T * VX_E)
 #define VX_RB 9
 #define VX_BINS (1 << VX_RB)
-#define VX_PE 4                          /* sorted positions per thread and tile of the run-head pass */
-#define VX_OV 64                         /* positions staged past the end of a tile: a run that starts in the tile usually ends there */
-static_assert(VX_T == VX_BINS, "one digit per thread in the bin scans");
+#define VX_MAXPASS 4
+static_assert(VX_T == VX_BINS, "one digit per thread in the digit scans");
 
-#define VX_KT (VX_T * 4)                  /* pixels per tile of the key pass */
-struct __align__(128) VxSmem {
-    /* staging, by phase (the phases never overlap): raw tiles arrive here by bulk async copies (TMA, completion on mbar) */
-    union {
-        float4 kg[2][VX_KT];                                            /* key pass: levelled points of a tile, double-buffered */
-        struct { unsigned k[2][VX_TILE], v[2][VX_TILE]; } so;           /* sort pass: (voxel index, pixel) of a tile, double-buffered */
-        struct {
-            float4 pt[VX_T * VX_PE + VX_OV];                            /* run pass: the tile's points {x, y, z, pixel} in sorted order */
-            unsigned pk[VX_T * VX_PE + VX_OV + 1];                      /*           their voxel indices; [0] = the key before the tile */
-            int heads[VX_T * VX_PE];                                    /*           run heads of the tile, in order */
-        } pi;
-    } u;
-    unsigned wc[VX_NW][VX_BINS];         /* per-warp digit counters of a tile, then the warps' scatter offsets */
-    unsigned hist[4][VX_BINS];           /* digit histograms of the (up to four) passes */
-    unsigned binoff[VX_BINS];            /* running offset of every digit of the current pass */
-    int wsum[VX_NW + 1];
-    int wsum3[33];                       /* sp_block_scan_flags3 keeps its total in [32] */
-    SpFrameGrid g;
-    int vbits, npass;
-    unsigned long long mbar[2];
-};
+__device__ __forceinline__ size_t vx_slice(const SpDev &d, int f) { return (size_t)f * (size_t)((d.N + 3) & ~3); }
 
-/* contiguous global -> shared bulk copy (TMA, SASS UBLKCP); bytes a multiple of 16, both ends 16-byte aligned */
-__device__ __forceinline__ void vx_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+/* voxel grid of each frame: getMinMax3D result -> min_b, div_b, divb_mul (voxel_grid_indices.hpp:292-318), the "<100 points" guard
+ * of process() (StairPerception.cpp:56), and what the sort needs to know about the frame */
+__global__ void k_vx_grid(SpDev d, int nB, int force_bits)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(st_sptr(dst)), "l"(src), "r"(bytes), "r"(st_sptr(bar)) : "memory");
-}
-
-__device__ __forceinline__ int vx_block_excl(int v, int *ws, int *total)       /* exclusive block scan of an int, VX_T threads */
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    __syncthreads();
-    if (lane == 31) ws[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        const int x = lane < VX_NW ? ws[lane] : 0;
-        int xi = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
-        if (lane < VX_NW) ws[lane] = xi - x;
-        if (lane == 31) ws[VX_NW] = xi;
-    }
-    __syncthreads();
-    *total = ws[VX_NW];
-    return ws[wid] + inc - v;
-}
-
-__global__ void __launch_bounds__(VX_T, 2) k_voxel_frame(SpDev d, int force_bits)
-{
-    extern __shared__ __align__(128) unsigned char vx_raw[];
-    VxSmem &s = *reinterpret_cast<VxSmem *>(vx_raw);
-    const int f = blockIdx.x, N = d.N;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const size_t base = (size_t)f * N;
-    const size_t sbase = (size_t)f * (size_t)((N + 3) & ~3);             /* the frame's slice of the sort arrays (16-byte aligned) */
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nB) return;
     int *cnts = d.counts + f * SP_NCOUNT;
-    if (tid == 0) {
-        st_mbar_init(&s.mbar[0], 1); st_mbar_init(&s.mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    unsigned ph = 0;                                                         /* bit b = parity the next wait on mbar[b] expects */
-
-    /* ---- 1. the frame's grid (k_frame_grid of round 1) */
-    if (tid == 0) {
-        SpFrameGrid g;
-        g.status = 0; g.cells = 0; g.sorted_in_b = 0;
-        for (int k = 0; k < 3; ++k) { g.minb[k] = 0; g.mul[k] = 0; }
-        const int ncrop = cnts[2];
-        if (ncrop < 100) g.status = 1;                                       /* StairPerception.cpp:56 */
+    SpFrameGrid g;
+    g.status = 0; g.cells = 0; g.sorted_in_b = 0; g.npass = 0; g.M = 0;
+    for (int k = 0; k < 3; ++k) { g.minb[k] = 0; g.mul[k] = 0; }
+    const int ncrop = cnts[2];
+    if (ncrop < 100) g.status = 1;
+    else {
+        const int *mm = d.mm + f * 8;
+        const float mnx = sp_ord2f(mm[0]), mny = sp_ord2f(mm[1]), mnz = sp_ord2f(mm[2]);
+        const float mxx = sp_ord2f(mm[3]), mxy = sp_ord2f(mm[4]), mxz = sp_ord2f(mm[5]);
+        const long long dx = (long long)((mxx - mnx) * d.c.ivx) + 1, dy = (long long)((mxy - mny) * d.c.ivy) + 1,
+                        dz = (long long)((mxz - mnz) * d.c.ivz) + 1;
+        if (dx * dy * dz > 2147483647LL) g.status = 2;
         else {
-            const int *mm = d.mm + f * 8;
-            const float mnx = sp_ord2f(mm[0]), mny = sp_ord2f(mm[1]), mnz = sp_ord2f(mm[2]);
-            const float mxx = sp_ord2f(mm[3]), mxy = sp_ord2f(mm[4]), mxz = sp_ord2f(mm[5]);
-            const long long dx = (long long)((mxx - mnx) * d.c.ivx) + 1, dy = (long long)((mxy - mny) * d.c.ivy) + 1,
-                            dz = (long long)((mxz - mnz) * d.c.ivz) + 1;
-            if (dx * dy * dz > 2147483647LL) g.status = 2;                   /* voxel_grid_indices.hpp:295-303 */
-            else {
-                g.minb[0] = (int)floorf(mnx * d.c.ivx); g.minb[1] = (int)floorf(mny * d.c.ivy); g.minb[2] = (int)floorf(mnz * d.c.ivz);
-                const int m0 = (int)floorf(mxx * d.c.ivx), m1 = (int)floorf(mxy * d.c.ivy);
-                const int d0 = m0 - g.minb[0] + 1, d1 = m1 - g.minb[1] + 1;
-                g.mul[0] = 1; g.mul[1] = d0; g.mul[2] = d0 * d1;
-                /* bound of the voxel indices formed below (floor differences, one more than dx, dy, dz at most); a product past
-                 * int range means wrapped indices that need all 32 bits */
-                const long long d2 = (long long)((int)floorf(mxz * d.c.ivz) - g.minb[2] + 1);
-                const long long cells = (long long)d0 * d1 * d2;
-                g.cells = cells > 2147483647LL ? -1 : (int)cells;
-            }
+            g.minb[0] = (int)floorf(mnx * d.c.ivx); g.minb[1] = (int)floorf(mny * d.c.ivy); g.minb[2] = (int)floorf(mnz * d.c.ivz);
+            const int m0 = (int)floorf(mxx * d.c.ivx), m1 = (int)floorf(mxy * d.c.ivy);
+            const int d0 = m0 - g.minb[0] + 1, d1 = m1 - g.minb[1] + 1;
+            g.mul[0] = 1; g.mul[1] = d0; g.mul[2] = d0 * d1;
+            /* bound of the voxel indices k_vx_key forms (floor differences, one more than dx, dy, dz at most); a product past
+             * int range means wrapped indices that need all 32 bits */
+            const long long d2 = (long long)((int)floorf(mxz * d.c.ivz) - g.minb[2] + 1);
+            const long long cells = (long long)d0 * d1 * d2;
+            g.cells = cells > 2147483647LL ? -1 : (int)cells;
         }
+    }
+    if (g.status == 0) {
         int vbits = 1;
         while (vbits < 32 && (g.cells < 0 || (1LL << vbits) < (long long)g.cells)) ++vbits;
         if (force_bits > vbits) vbits = min(32, force_bits);
-        const int npass = (vbits + VX_RB - 1) / VX_RB;
-        g.sorted_in_b = npass & 1;
-        s.g = g; s.vbits = vbits; s.npass = npass;
-        d.grid[f] = g;
-        cnts[0] = g.status;
+        g.npass = (vbits + VX_RB - 1) / VX_RB;
+        g.sorted_in_b = g.npass & 1;
+        g.M = ncrop;
     }
-    for (int k = tid; k < 4 * VX_BINS; k += VX_T) (&s.hist[0][0])[k] = 0u;
+    d.grid[f] = g;
+    cnts[0] = g.status;
+}
+
+/* Only the cropped points go through the sort.  K1K2 left the number of cropped pixels per 1024-pixel block in vcnt; this
+ * kernel turns them into offsets inside the frame's slice (one CTA per frame) */
+__global__ void __launch_bounds__(256) k_vx_offsets(SpDev d)
+{
+    __shared__ int ws[8];
+    __shared__ int carry;
+    const int f = blockIdx.x, nblk = d.nblk;
+    const bool live = d.grid[f].status == 0;
+    const int *cnt = d.vcnt + (size_t)f * nblk;
+    int *off = d.voff + (size_t)f * nblk;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const SpFrameGrid g = s.g;
-    if (g.status != 0) {                                                     /* process() returns before the voxel filter */
-        if (tid == 0) { cnts[3] = 0; cnts[4] = 0; cnts[5] = 0; cnts[6] = 0; cnts[7] = 0; d.seg_n[2 * f] = 0; d.seg_n[2 * f + 1] = 0; }
-        return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblk; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        const int v = (live && b < nblk) ? cnt[b] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) ws[wid] = inc;
+        __syncthreads();
+        int add = carry;
+        for (int w = 0; w < wid; ++w) add += ws[w];
+        if (b < nblk) off[b] = add + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = add + inc;
+        __syncthreads();
     }
-    const int npass = s.npass;
-    unsigned *ka = reinterpret_cast<unsigned *>(d.key_a) + sbase, *kb = reinterpret_cast<unsigned *>(d.key_b) + sbase;
-    unsigned *va = d.val_a + sbase, *vb = d.val_b + sbase;
+}
+
+
+/* voxel index per cropped point (voxel_grid_indices.hpp:378-394), written compacted in pixel order: one CTA per 1024 pixels */
+__global__ void __launch_bounds__(256) k_vx_key(SpDev d)
+{
+    __shared__ int wsum[33];
+    const int f = blockIdx.y, N = d.N;
+    const SpFrameGrid g = d.grid[f];
+    if (g.status != 0) return;
+    unsigned *ka = reinterpret_cast<unsigned *>(d.key_a) + vx_slice(d, f);
+    unsigned *va = d.val_a + vx_slice(d, f);
+    int pos = d.voff[(size_t)f * d.nblk + blockIdx.x];
+    for (int q = 0; q < 4; ++q) {
+        const int i = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+        bool ok = false; unsigned key = 0;
+        if (i < N) {
+            const float4 pw = d.xyzw[(size_t)f * N + i];
+            const float px = pw.x, py = pw.y, pz = pw.z;
+            if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
+                const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
+                const int b = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
+                const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
+                key = (unsigned)(a * g.mul[0] + b * g.mul[1] + c * g.mul[2]);
+                ok = true;
+            }
+        }
+        int tot;
+        const int r = sp_block_scan_flag(ok, wsum, &tot);
+        if (ok) { ka[pos + r] = key; va[pos + r] = (unsigned)i; }
+        pos += tot;
+    }
+}
+
+/* ---- the sort: pass p reads buffer a (p even) or b (p odd) of the frame's slice and writes the other one ---------------------- */
+/* digit histogram of one tile */
+__global__ void __launch_bounds__(VX_T) k_vx_hist(SpDev d, int p)
+{
+    __shared__ unsigned h[VX_BINS];
+    const int f = blockIdx.y, tile = blockIdx.x;
+    const SpFrameGrid g = d.grid[f];
+    if (p >= g.npass || tile * VX_TILE >= g.M) return;
+    const unsigned *sk = reinterpret_cast<const unsigned *>((p & 1) ? d.key_b : d.key_a) + vx_slice(d, f);
+    const int shift = p * VX_RB, j1 = min(g.M, (tile + 1) * VX_TILE);
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int j = tile * VX_TILE + threadIdx.x; j < j1; j += VX_T) atomicAdd(&h[(sk[j] >> shift) & (VX_BINS - 1)], 1u);
+    __syncthreads();
+    d.vth[((size_t)f * d.ntile + tile) * VX_BINS + threadIdx.x] = h[threadIdx.x];
+}
+
+/* (tile, digit) counts of a frame -> first destination of every tile's keys of every digit: digit-major, tile-minor (one CTA per frame) */
+__global__ void __launch_bounds__(VX_T) k_vx_scan(SpDev d, int p)
+{
+    __shared__ int ws[VX_NW + 1];
+    const int f = blockIdx.x;
+    const SpFrameGrid g = d.grid[f];
+    if (p >= g.npass) return;
+    const int nt = (g.M + VX_TILE - 1) / VX_TILE, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned *th = d.vth + (size_t)f * d.ntile * VX_BINS;
+    unsigned tot = 0;
+    for (int t = 0; t < nt; ++t) tot += th[(size_t)t * VX_BINS + tid];
+    int inc = (int)tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    int add = 0;
+    for (int w = 0; w < wid; ++w) add += ws[w];
+    unsigned run = (unsigned)(add + inc) - tot;
+    for (int t = 0; t < nt; ++t) { const unsigned c = th[(size_t)t * VX_BINS + tid]; th[(size_t)t * VX_BINS + tid] = run; run += c; }
+}
+
+/* one tile: stable rank of every key among the tile's keys of the same digit, then the scatter */
+__global__ void __launch_bounds__(VX_T) k_vx_scatter(SpDev d, int p)
+{
+    __shared__ unsigned wc[VX_NW][VX_BINS];
+    const int f = blockIdx.y, tile = blockIdx.x;
+    const SpFrameGrid g = d.grid[f];
+    if (p >= g.npass || tile * VX_TILE >= g.M) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, M = g.M;
+    const unsigned lt = (1u << lane) - 1u;
+    const size_t sl = vx_slice(d, f);
+    const unsigned *sk = reinterpret_cast<const unsigned *>((p & 1) ? d.key_b : d.key_a) + sl, *sv = ((p & 1) ? d.val_b : d.val_a) + sl;
+    unsigned *dk = reinterpret_cast<unsigned *>((p & 1) ? d.key_a : d.key_b) + sl, *dv = ((p & 1) ? d.val_a : d.val_b) + sl;
+    const int shift = p * VX_RB;
+    for (int k = lane; k < VX_BINS; k += 32) wc[wid][k] = 0u;
+    const int cb = tile * VX_TILE + wid * (32 * VX_E);                       /* warp-striped: position order = (warp, k, lane) */
+    unsigned key[VX_E], val[VX_E], rank[VX_E];
+#pragma unroll
+    for (int k = 0; k < VX_E; ++k) { const int j = cb + k * 32 + lane; key[k] = j < M ? sk[j] : 0u; val[k] = j < M ? sv[j] : 0u; }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < VX_E; ++k) {
+        const int j = cb + k * 32 + lane;
+        const unsigned dg = (key[k] >> shift) & (VX_BINS - 1);
+        const unsigned m = __match_any_sync(0xffffffffu, j < M ? dg : (unsigned)VX_BINS + lane);
+        unsigned prev = 0;
+        if (j < M) prev = wc[wid][dg];
+        __syncwarp();
+        if (j < M && (m & lt) == 0) wc[wid][dg] = prev + __popc(m);
+        __syncwarp();
+        rank[k] = prev + __popc(m & lt);
+    }
+    __syncthreads();
+    {                                                                        /* digit tid: where each warp's keys of this tile go */
+        unsigned run = d.vth[((size_t)f * d.ntile + tile) * VX_BINS + tid];
+#pragma unroll
+        for (int w = 0; w < VX_NW; ++w) { const unsigned c = wc[w][tid]; wc[w][tid] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VX_E; ++k) {
+        const int j = cb + k * 32 + lane;
+        if (j < M) {
+            const unsigned pos = wc[wid][(key[k] >> shift) & (VX_BINS - 1)] + rank[k];
+            dk[pos] = key[k]; dv[pos] = val[k];
+        }
+    }
+}
+
+/* After the stable radix sort: one thread per sorted position.  The thread at the head of a run of equal keys
+ * walks the run: sequential float centroid (pcl::CentroidPoint), first strictly-nearest point
+ * (voxel_grid_indices.hpp:489-513), then the three point filters a6-a8 (StairPerception.cpp:598-713) on the
+ * representative.  Per-1024-block class counts feed the list scatter. */
+__global__ void __launch_bounds__(256) k_vx_pick(SpDev d)
+{
+    __shared__ int cnt[5];
+    const int f = blockIdx.y, N = d.N;
+    const size_t base = (size_t)f * N;
+    if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const SpFrameGrid g = d.grid[f];
+    const int M = g.M;                                             /* this frame's cropped points, sorted by voxel (0 when process() stopped) */
+    const unsigned *keys = reinterpret_cast<const unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + vx_slice(d, f);
+    const unsigned *vals = (g.sorted_in_b ? d.val_b : d.val_a) + vx_slice(d, f);
     const float4 *P = d.xyzw + base;
-
-    /* ---- 2. voxel index per cropped point, compacted in pixel order (warp-striped tiles: position order = (warp, k, lane)).
-     * The levelled points of tile i + 1 are in flight (bulk copy) while tile i is processed */
-    int M = 0;
-    {
-        const int nkt = (N + VX_KT - 1) / VX_KT;
-        if (tid == 0) {
-            const unsigned bytes = (unsigned)min(VX_KT, N) * 16u;
-            st_mbar_expect(&s.mbar[0], bytes);
-            vx_bulk(&s.u.kg[0][0], P, bytes, &s.mbar[0]);
-        }
-        for (int it = 0; it < nkt; ++it) {
-            const int t0 = it * VX_KT, b = it & 1;
-            if (tid == 0 && it + 1 < nkt) {                                  /* buffer b ^ 1 was consumed before the last barrier */
-                const unsigned bytes = (unsigned)min(VX_KT, N - (t0 + VX_KT)) * 16u;
-                st_mbar_expect(&s.mbar[b ^ 1], bytes);
-                vx_bulk(&s.u.kg[b ^ 1][0], P + t0 + VX_KT, bytes, &s.mbar[b ^ 1]);
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    for (int q = 0; q < 4; ++q) {
+        const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+        if (j >= M) break;
+        unsigned char code = 0; int rep = -1;
+        const unsigned key = keys[j];
+        if (j == 0 || keys[j - 1] != key) {
+            float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
+            for (int t = j; t < M && keys[t] == key; ++t) { const float4 pw = P[vals[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
+            const float fn = (float)n;
+            const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
+            float best = FLT_MAX;
+            for (int t = j; t < j + n; ++t) {
+                const unsigned p = vals[t];
+                const float4 pw = P[p];
+                const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
+                const float dis = dx * dx + dy * dy + dz * dz;
+                if (best > dis) { best = dis; rep = (int)p; }
             }
-            st_mbar_wait(&s.mbar[b], (ph >> b) & 1u); ph ^= 1u << b;
-            const int cl = wid * (32 * 4);
-            unsigned key[4];
-            unsigned okm = 0;
-            int rank[4], cnt = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int q = cl + k * 32 + lane, i = t0 + q;
-                bool ok = false; unsigned ky = 0;
-                if (i < N) {
-                    const float4 pw = s.u.kg[b][q];
-                    const float px = pw.x, py = pw.y, pz = pw.z;
-                    if (sp_finite3(px, py, pz) && !(px < d.c.x0 || px > d.c.x1) && !(py < d.c.y0 || py > d.c.y1) && !(pz < d.c.z0 || pz > d.c.z1)) {
-                        const int a = (int)(floorf(px * d.c.ivx) - (float)g.minb[0]);
-                        const int bq = (int)(floorf(py * d.c.ivy) - (float)g.minb[1]);
-                        const int c = (int)(floorf(pz * d.c.ivz) - (float)g.minb[2]);
-                        ky = (unsigned)(a * g.mul[0] + bq * g.mul[1] + c * g.mul[2]);
-                        ok = true;
-                    }
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                key[k] = ky; rank[k] = cnt + __popc(bal & lt); cnt += __popc(bal);
-                if (ok) okm |= 1u << k;
-            }
-            int tot;
-            const int wbase = vx_block_excl(lane == 0 ? cnt : 0, s.wsum, &tot);   /* lane 0 of each warp carries the warp's count */
-            const int wb = __shfl_sync(0xffffffffu, wbase, 0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (okm & (1u << k)) {
-                    const int pos = M + wb + rank[k];
-                    ka[pos] = key[k]; va[pos] = (unsigned)(t0 + cl + k * 32 + lane);
-                    for (int p = 0; p < npass; ++p) atomicAdd(&s.hist[p][(key[k] >> (p * VX_RB)) & (VX_BINS - 1)], 1u);
+            code = SPC_HEAD; ++c0;
+            const float4 nw = d.nrm[base + rep];
+            const float nx = nw.x, ny = nw.y, nz = nw.z;
+            if (sp_finite3(nx, ny, nz)) {
+                code |= SPC_NONAN; ++c1;
+                const float4 pw = P[rep];
+                const float px = pw.x, py = pw.y, pz = pw.z;
+                if (px * px + py * py + pz * pz > d.c.noleg_th2) {
+                    code |= SPC_NOLEG; ++c2;
+                    if (nx >= d.c.h_ge || nx <= d.c.h_le) { code |= SPC_H; ++c3; }
+                    else if (nx >= d.c.v_lo && nx <= d.c.v_hi) { code |= SPC_V; ++c4; }
                 }
             }
-            M += tot;
         }
+        d.rep[base + j] = rep; d.code[base + j] = code;                       /* positions past M are never read */
     }
-    asm volatile("fence.proxy.async;" ::: "memory");                        /* the pairs written above are read by bulk copies below */
+    c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
+    c3 = __reduce_add_sync(0xffffffffu, c3); c4 = __reduce_add_sync(0xffffffffu, c4);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); atomicAdd(&cnt[2], c2); atomicAdd(&cnt[3], c3); atomicAdd(&cnt[4], c4); }
     __syncthreads();
+    if (threadIdx.x < 5) d.blk[((size_t)f * d.nblk + blockIdx.x) * 5 + threadIdx.x] = cnt[threadIdx.x];
+}
 
-    /* ---- 3. stable LSD radix sort; tile i + 1 of the source is in flight while tile i is ranked and scattered */
-    for (int p = 0; p < npass; ++p) {
-        const unsigned *sk = (p & 1) ? kb : ka, *sv = (p & 1) ? vb : va;
-        unsigned *dk = (p & 1) ? ka : kb, *dv = (p & 1) ? va : vb;
-        const int shift = p * VX_RB;
-        const int nt = (M + VX_TILE - 1) / VX_TILE;
-        if (tid == 0) {
-            const unsigned bytes = ((unsigned)min(VX_TILE, M) * 4u + 15u) & ~15u;
-            st_mbar_expect(&s.mbar[0], 2 * bytes);
-            vx_bulk(&s.u.so.k[0][0], sk, bytes, &s.mbar[0]);
-            vx_bulk(&s.u.so.v[0][0], sv, bytes, &s.mbar[0]);
-        }
-        {
-            int tot;
-            const int e = vx_block_excl((int)s.hist[p][tid], s.wsum, &tot);       /* VX_T == VX_BINS: one digit per thread */
-            s.binoff[tid] = (unsigned)e;
-        }
-        for (int k = lane; k < VX_BINS; k += 32) s.wc[wid][k] = 0u;
+/* exclusive scan of the per-block counts of one frame (one CTA per frame) + frame totals */
+__global__ void __launch_bounds__(256) k_scan_blocks(SpDev d)
+{
+    __shared__ int carry[5];
+    __shared__ int ws[5][8];
+    const int f = blockIdx.x, nblk = d.nblk;
+    int *blk = d.blk + (size_t)f * nblk * 5;
+    if (threadIdx.x < 5) carry[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblk; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        int v[5], inc[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { v[k] = b < nblk ? blk[b * 5 + k] : 0; inc[k] = v[k]; }
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc[k], o); if (lane >= o) inc[k] += t; }
+        if (lane == 31) { for (int k = 0; k < 5; ++k) ws[k][wid] = inc[k]; }
         __syncthreads();
-        for (int it = 0; it < nt; ++it) {
-            const int t0 = it * VX_TILE, b = it & 1;
-            if (tid == 0 && it + 1 < nt) {
-                const unsigned bytes = ((unsigned)min(VX_TILE, M - (t0 + VX_TILE)) * 4u + 15u) & ~15u;
-                st_mbar_expect(&s.mbar[b ^ 1], 2 * bytes);
-                vx_bulk(&s.u.so.k[b ^ 1][0], sk + t0 + VX_TILE, bytes, &s.mbar[b ^ 1]);
-                vx_bulk(&s.u.so.v[b ^ 1][0], sv + t0 + VX_TILE, bytes, &s.mbar[b ^ 1]);
-            }
-            st_mbar_wait(&s.mbar[b], (ph >> b) & 1u); ph ^= 1u << b;
-            const int cl = wid * (32 * VX_E), cb = t0 + cl;
-            unsigned key[VX_E], val[VX_E], rank[VX_E];
+        int add[5];
 #pragma unroll
-            for (int k = 0; k < VX_E; ++k) { key[k] = s.u.so.k[b][cl + k * 32 + lane]; val[k] = s.u.so.v[b][cl + k * 32 + lane]; }
-#pragma unroll
-            for (int k = 0; k < VX_E; ++k) {
-                const int j = cb + k * 32 + lane;
-                const unsigned dg = (key[k] >> shift) & (VX_BINS - 1);
-                const unsigned m = __match_any_sync(0xffffffffu, j < M ? dg : (unsigned)VX_BINS + lane);
-                unsigned prev = 0;
-                if (j < M) prev = s.wc[wid][dg];
-                __syncwarp();
-                if (j < M && (m & lt) == 0) s.wc[wid][dg] = prev + __popc(m);
-                __syncwarp();
-                rank[k] = prev + __popc(m & lt);
-            }
-            __syncthreads();
-            {                                                                /* digit tid: where each warp's elements of this tile go */
-                unsigned run = s.binoff[tid];
-#pragma unroll
-                for (int w = 0; w < VX_NW; ++w) { const unsigned c = s.wc[w][tid]; s.wc[w][tid] = run; run += c; }
-                s.binoff[tid] = run;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < VX_E; ++k) {
-                const int j = cb + k * 32 + lane;
-                if (j < M) {
-                    const unsigned dg = (key[k] >> shift) & (VX_BINS - 1);
-                    const unsigned pos = s.wc[wid][dg] + rank[k];
-                    dk[pos] = key[k]; dv[pos] = val[k];
-                }
-            }
-            __syncwarp();
-            for (int k = lane; k < VX_BINS; k += 32) s.wc[wid][k] = 0u;      /* the warp's own row, for the next tile */
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");                    /* the next pass reads what this one wrote by bulk copies */
+        for (int k = 0; k < 5; ++k) { int a = carry[k]; for (int w = 0; w < wid; ++w) a += ws[k][w]; add[k] = a; }
+        if (b < nblk) { for (int k = 0; k < 5; ++k) blk[b * 5 + k] = add[k] + inc[k] - v[k]; }
+        __syncthreads();
+        if (threadIdx.x == 255) { for (int k = 0; k < 5; ++k) carry[k] = add[k] + inc[k]; }
         __syncthreads();
     }
-
-    /* ---- 4. voxels = runs of equal keys; representative + class per voxel; ordered lists */
-    const unsigned *K = (npass & 1) ? kb : ka, *V = (npass & 1) ? vb : va;
-    const size_t sH = (size_t)(2 * f) * N, sV = (size_t)(2 * f + 1) * N;
-    int nvox = 0, nnonan = 0, nnoleg = 0, nH = 0, nV = 0;                    /* CTA-uniform running totals */
-    for (int t0 = 0; t0 < M; t0 += VX_T * VX_PE) {
-        /* stage the tile: one parallel gather per sorted position (the run walks below then read shared memory, not a chain of
-         * dependent global loads) */
-        const int nst = min(M - t0, VX_T * VX_PE + VX_OV);
-        {
-            unsigned vv[VX_PE + 1], kq[VX_PE + 1];
-#pragma unroll
-            for (int k = 0; k <= VX_PE; ++k) { const int q = tid + k * VX_T; vv[k] = 0u; kq[k] = 0u; if (q < nst) { vv[k] = V[t0 + q]; kq[k] = K[t0 + q]; } }
-#pragma unroll
-            for (int k = 0; k <= VX_PE; ++k) {
-                const int q = tid + k * VX_T;
-                if (q < nst) { float4 pw = P[vv[k]]; pw.w = __uint_as_float(vv[k]); s.u.pi.pt[q] = pw; s.u.pi.pk[q + 1] = kq[k]; }
-            }
-            if (tid == 0) s.u.pi.pk[0] = t0 > 0 ? K[t0 - 1] : 0u;
-        }
-        __syncthreads();
-        /* heads of this tile, in order */
-        int hcnt = 0;
-        bool hd[VX_PE];
-#pragma unroll
-        for (int k = 0; k < VX_PE; ++k) {
-            const int q = tid * VX_PE + k, j = t0 + q;
-            hd[k] = j < M && (j == 0 || s.u.pi.pk[q] != s.u.pi.pk[q + 1]);
-            hcnt += hd[k] ? 1 : 0;
-        }
-        int nh;
-        int hp = vx_block_excl(hcnt, s.wsum, &nh);
-#pragma unroll
-        for (int k = 0; k < VX_PE; ++k) if (hd[k]) s.u.pi.heads[hp++] = tid * VX_PE + k;
-        __syncthreads();
-        for (int u0 = 0; u0 < nh; u0 += VX_T) {
-            const int u = u0 + tid;
-            bool fNN = false, fNL = false, fH = false, fV = false;
-            int rep = -1; unsigned char code = 0;
-            float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (u < nh) {
-                const int q0 = s.u.pi.heads[u];
-                const unsigned key = s.u.pi.pk[q0 + 1];
-                float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-                int q = q0;
-                for (; q < nst && s.u.pi.pk[q + 1] == key; ++q) { const float4 pw = s.u.pi.pt[q]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
-                if (q == nst) for (int t = t0 + q; t < M && K[t] == key; ++t) { const float4 pw = P[V[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }   /* a run past the staged part */
-                const float fn = (float)n;
-                const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
-                float best = FLT_MAX;
-                for (int e = 0; e < n; ++e) {
-                    float4 pw;
-                    if (q0 + e < nst) pw = s.u.pi.pt[q0 + e];
-                    else { const unsigned p = V[t0 + q0 + e]; pw = P[p]; pw.w = __uint_as_float(p); }
-                    const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
-                    const float dis = dx * dx + dy * dy + dz * dz;
-                    if (best > dis) { best = dis; rp = pw; }
-                }
-                rep = (int)__float_as_uint(rp.w);
-                code = SPC_HEAD;
-                const float4 nw = d.nrm[base + rep];
-                const float nx = nw.x, ny = nw.y, nz = nw.z;
-                if (sp_finite3(nx, ny, nz)) {
-                    code |= SPC_NONAN; fNN = true;
-                    if (rp.x * rp.x + rp.y * rp.y + rp.z * rp.z > d.c.noleg_th2) {
-                        code |= SPC_NOLEG; fNL = true;
-                        if (nx >= d.c.h_ge || nx <= d.c.h_le) { code |= SPC_H; fH = true; }
-                        else if (nx >= d.c.v_lo && nx <= d.c.v_hi) { code |= SPC_V; fV = true; }
-                    }
-                }
-                d.voxel_idx[base + nvox + u] = rep; d.voxel_code[base + nvox + u] = code;
-            }
-            int tot3;
-            const int pk3 = sp_block_scan_flags3(fH, fV, fNN, s.wsum3, &tot3);  /* 10-bit fields: VX_T = 512 < 1023 */
-            const int cNL = __syncthreads_count(fNL);
-            if (fH) d.pts[sH + nH + (pk3 & 1023)] = rp;                          /* {x, y, z, pixel} */
-            if (fV) d.pts[sV + nV + ((pk3 >> 10) & 1023)] = rp;
-            nH += tot3 & 1023; nV += (tot3 >> 10) & 1023; nnonan += tot3 >> 20; nnoleg += cNL;
-        }
-        nvox += nh;
-        __syncthreads();                                                     /* heads[] and the staged tile are rewritten by the next tile */
+    if (threadIdx.x == 0) {
+        int *c = d.counts + f * SP_NCOUNT;
+        c[3] = carry[0]; c[4] = carry[1]; c[5] = carry[2]; c[6] = carry[3]; c[7] = carry[4];
+        d.seg_n[2 * f] = carry[3]; d.seg_n[2 * f + 1] = carry[4];
     }
-    if (tid == 0) {
-        cnts[3] = nvox; cnts[4] = nnonan; cnts[5] = nnoleg; cnts[6] = nH; cnts[7] = nV;
-        d.seg_n[2 * f] = nH; d.seg_n[2 * f + 1] = nV;
+}
+
+/* ordered scatter: voxel representative list (+ class code) and the horizontal / vertical point sets */
+__global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
+{
+    __shared__ int wsum[33];
+    const int f = blockIdx.y, N = d.N;
+    const size_t base = (size_t)f * N;
+    const int M = d.grid[f].M;                                            /* sorted positions of this frame */
+    if (blockIdx.x * 1024 >= M) return;
+    const int *blk = d.blk + ((size_t)f * d.nblk + blockIdx.x) * 5;
+    int b_head = blk[0], b_h = blk[3], b_v = blk[4];
+    for (int q = 0; q < 4; ++q) {
+        const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
+        const unsigned char code = j < M ? d.code[base + j] : 0;
+        const int rep = j < M ? d.rep[base + j] : -1;
+        int tot;
+        const int pk = sp_block_scan_flags3((code & SPC_HEAD) != 0, (code & SPC_H) != 0, (code & SPC_V) != 0, wsum, &tot);
+        const int ph = pk & 1023, pH = (pk >> 10) & 1023, pV = pk >> 20;
+        if (code & SPC_HEAD) { d.voxel_idx[base + b_head + ph] = rep; d.voxel_code[base + b_head + ph] = code; }
+        if (code & SPC_H) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f) * N + b_h + pH] = pw; }
+        if (code & SPC_V) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f + 1) * N + b_v + pV] = pw; }
+        b_head += tot & 1023; b_h += (tot >> 10) & 1023; b_v += tot >> 20;
     }
 }
