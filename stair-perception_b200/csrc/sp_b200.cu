@@ -139,6 +139,13 @@ struct sp_ctx {
     std::vector<cudaEvent_t> tev;
     std::vector<const char *> tname;
     int tn = 0;
+    /* CUDA graphs of the chunk pipeline for small single-chunk calls (the reference's one-frame-per-call mode): the ~35 launches of
+     * a chunk become one graph launch.  Keyed by everything baked into the nodes; SP_GRAPH=0 switches it off. */
+    struct ChunkGraph { const void *din; const void *dR; const void *res; int nB, show_mode; cudaGraphExec_t exec; uint64_t used; int64_t launches; };
+    std::vector<ChunkGraph> graphs;
+    uint64_t graph_clock = 0;
+    int graph_max_frames = 8;
+    bool capturing = false;
     int last_nB = 0;
     sp_frame_result *last_res = nullptr;      /* device records of the last chunk: the lane's own array, or a slice of the batch array */
     sp_frame_result *d_batch_res = nullptr;   /* records of a whole batch on the device (compact entry point), grown on demand */
@@ -175,7 +182,7 @@ int frame_bits(int B) { int b = 0; while ((1 << b) < B) ++b; return b; }
 /* trace mark: an event after the launch(es) named `name` (no-op unless tracing) */
 void mark(sp_ctx *ctx, const char *name)
 {
-    if (!ctx->trace) return;
+    if (!ctx->trace || ctx->capturing) return;
     if (ctx->tn >= (int)ctx->tev.size()) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -198,7 +205,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     ctx->tn = 0;
     const bool all = only_stage < 0 || only_stage == 2;
     mark(ctx, "begin");
-    CK(cudaEventRecord(ctx->ev[0], st));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[0], st));
     if ((all || only_stage == 0) && ctx->normal_mode == 0) {
         k_init_frames<<<(nB * SP_NCOUNT + 255) / 256, 256, 0, st>>>(d, nB);
         mark(ctx, "k_init_frames");
@@ -268,7 +275,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_knn_normals");
         ctx->launches += 6 + 2 * (2 + 2 + (32 + frame_bits(nB) + 7) / 8);
     }
-    CK(cudaEventRecord(ctx->ev[1], st));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[1], st));
     const bool want_voxel = (all && show_mode >= SP_SHOW_VOXEL) || only_stage == 1;
     if (want_voxel) {
         /* no host round trip: the per-frame sizes and pass counts stay on the device (SpFrameGrid) */
@@ -291,7 +298,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_scatter_lists");
         ctx->launches += 6 + 3 * VX_MAXPASS;
     }
-    CK(cudaEventRecord(ctx->ev[2], st));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
     const int seg_gx = std::max(SEG_GRID_X, std::min(592, N / 8192));     /* CTAs per segment: big single clouds need more */
     if (want_seg) {
@@ -313,7 +320,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_cl_rank");
         ctx->launches += 7;
     }
-    CK(cudaEventRecord(ctx->ev[3], st));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3], st));
     if (want_seg) {
         k_clear_planes<<<(2 * nB * SP_PSEG + 255) / 256, 256, 0, st>>>(d, 2 * nB);
         mark(ctx, "k_clear_planes");
@@ -321,7 +328,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_ransac");
         ctx->launches += 2;
     }
-    CK(cudaEventRecord(ctx->ev[4], st));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[4], st));
     if (all) {
         if (want_seg) {
             k_merge<<<(nB + MG_WARPS - 1) / MG_WARPS, MG_WARPS * 32, 0, st>>>(d, nB);
@@ -339,7 +346,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
         mark(ctx, "k_gather_plane_points");
         ctx->launches += 2;
     }
-    CK(cudaEventRecord(ctx->ev[5], st));
+    if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaGetLastError());
     return SP_OK;
 }
@@ -369,6 +376,8 @@ int sp_set_params(sp_ctx *ctx, const sp_params *params)
         params->seg_max_iters < 0) { ERR(ctx) = "invalid parameters"; return SP_ERR_ARG; }
     ctx->params = *params;
     make_consts(*params, ctx->d.c);
+    for (auto &q : ctx->graphs) cudaGraphExecDestroy(q.exec);              /* the derived constants are baked into the recorded launches */
+    ctx->graphs.clear();
     for (sp_ctx *t = ctx->twin; t; t = t->twin) { t->params = *params; t->d.c = ctx->d.c; }
     return SP_OK;
 }
@@ -385,6 +394,7 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     sp_ctx *ctx = new sp_ctx();
     ctx->device = device; ctx->W = width; ctx->H = height; ctx->N = width * height; ctx->B = max_batch;
     { const char *t = getenv("SP_TRACE"); ctx->trace = t && *t && *t != '0'; }
+    { const char *t = getenv("SP_GRAPH"); if (t && *t) ctx->graph_max_frames = std::max(0, atoi(t)) == 0 ? 0 : std::max(1, atoi(t)); }
     { const char *t = getenv("SP_VBITS"); ctx->force_vbits = t && *t ? std::max(0, std::min(32, atoi(t))) : 0; }
     { const char *t = getenv("SP_NO_TWIN"); ctx->no_twin = t && *t && *t != '0'; }
     { const char *t = getenv("SP_LANES"); if (t && *t) ctx->want_lanes = std::max(1, std::min(4, atoi(t))); if (ctx->want_lanes < 2) ctx->no_twin = true; }
@@ -479,6 +489,8 @@ void sp_destroy(sp_ctx *ctx)
     if (ctx->twin) { sp_destroy(ctx->twin); ctx->twin = nullptr; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &q : ctx->graphs) cudaGraphExecDestroy(q.exec);
+    ctx->graphs.clear();
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->d_batch_res) cudaFree(ctx->d_batch_res);
     if (ctx->d_coff) cudaFree(ctx->d_coff);
@@ -648,7 +660,40 @@ static int process_impl(sp_ctx *ctx, const void *xyzrgba, const float *R9, int n
         }
         sp_frame_result *dres = keep_on_device ? ctx->d_batch_res + f0 : L->d.results;
         CK(cudaMemsetAsync(dres, 0, sizeof(sp_frame_result) * nB, L->stream));
-        const int rc = run_chunk(L, din, dR, nB, show_mode, -1, keep_on_device ? dres : nullptr);
+        int rc = SP_OK;
+        if (nchunks == 1 && nB <= ctx->graph_max_frames && !ctx->trace && L == ctx && ctx->normal_mode == 0) {
+            /* small single-chunk call: replay (or record once) the chunk's launch sequence as a CUDA graph */
+            sp_ctx::ChunkGraph *cg = nullptr;
+            for (auto &q : ctx->graphs) if (q.din == din && q.dR == dR && q.res == dres && q.nB == nB && q.show_mode == show_mode) cg = &q;
+            if (!cg) {
+                cudaGraph_t graph = nullptr;
+                const int64_t l0 = ctx->launches;
+                CK(cudaStreamBeginCapture(L->stream, cudaStreamCaptureModeThreadLocal));
+                ctx->capturing = true;
+                rc = run_chunk(L, din, dR, nB, show_mode, -1, keep_on_device ? dres : nullptr);
+                ctx->capturing = false;
+                const cudaError_t ce = cudaStreamEndCapture(L->stream, &graph);
+                if (rc == SP_OK && ce != cudaSuccess) { ERR(ctx) = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); rc = SP_ERR_CUDA; }
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                cudaGraphExec_t exec = nullptr;
+                const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) { ERR(ctx) = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie); return SP_ERR_CUDA; }
+                if (ctx->graphs.size() >= 8) {                             /* evict the least recently used */
+                    size_t lru = 0;
+                    for (size_t k = 1; k < ctx->graphs.size(); ++k) if (ctx->graphs[k].used < ctx->graphs[lru].used) lru = k;
+                    cudaGraphExecDestroy(ctx->graphs[lru].exec);
+                    ctx->graphs.erase(ctx->graphs.begin() + (long)lru);
+                }
+                ctx->graphs.push_back({ din, dR, dres, nB, show_mode, exec, 0, ctx->launches - l0 });
+                ctx->launches = l0;
+                cg = &ctx->graphs.back();
+            }
+            cg->used = ++ctx->graph_clock;
+            CK(cudaGraphLaunch(cg->exec, L->stream));
+            ctx->launches += cg->launches;
+            ctx->last_nB = nB; ctx->last_res = dres; ctx->tn = 0;
+        } else rc = run_chunk(L, din, dR, nB, show_mode, -1, keep_on_device ? dres : nullptr);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_done[buf], L->stream));
         if (!keep_on_device) {
@@ -865,6 +910,8 @@ int sp_set_normal_mode(sp_ctx *ctx, int mode)
         }
     }
     ctx->normal_mode = mode;
+    for (auto &q : ctx->graphs) cudaGraphExecDestroy(q.exec);
+    ctx->graphs.clear();
     return SP_OK;
 }
 

@@ -227,62 +227,112 @@ __global__ void __launch_bounds__(VX_T) k_vx_scatter(SpDev d, int p)
     }
 }
 
-/* After the stable radix sort: one thread per sorted position.  The thread at the head of a run of equal keys
- * walks the run: sequential float centroid (pcl::CentroidPoint), first strictly-nearest point
- * (voxel_grid_indices.hpp:489-513), then the three point filters a6-a8 (StairPerception.cpp:598-713) on the
- * representative.  Per-1024-block class counts feed the list scatter. */
-__global__ void __launch_bounds__(256) k_vx_pick(SpDev d)
+/* After the stable radix sort: runs of equal keys = voxels (voxel_grid_indices.hpp:411-422).  One CTA per 1024 sorted positions.
+ * The points of the tile (+ 64 positions past its end) are gathered ONCE, in parallel, into shared memory; the run heads are
+ * compacted so that every lane of a warp walks a run (a thread per position leaves two thirds of the lanes idle: runs are three
+ * points long on average): sequential float centroid (pcl::CentroidPoint), first strictly-nearest point (:489-513), then the three
+ * point filters a6-a8 (StairPerception.cpp:598-713) on the representative.  Per-1024-block class counts feed the list scatter. */
+#define VP_T 256
+#define VP_PE 4
+#define VP_TILE (VP_T * VP_PE)
+#define VP_OV 64
+__global__ void __launch_bounds__(VP_T) k_vx_pick(SpDev d)
 {
+    __shared__ float4 pt[VP_TILE + VP_OV];                               /* {x, y, z, pixel} in sorted order */
+    __shared__ unsigned pk[VP_TILE + VP_OV + 1];                         /* voxel indices; [0] = the key before the tile */
+    __shared__ unsigned short heads[VP_TILE];
+    __shared__ int wsum[33];
     __shared__ int cnt[5];
-    const int f = blockIdx.y, N = d.N;
+    const int f = blockIdx.y, N = d.N, tid = threadIdx.x;
     const size_t base = (size_t)f * N;
-    if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
-    __syncthreads();
     const SpFrameGrid g = d.grid[f];
-    const int M = g.M;                                             /* this frame's cropped points, sorted by voxel (0 when process() stopped) */
-    const unsigned *keys = reinterpret_cast<const unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + vx_slice(d, f);
-    const unsigned *vals = (g.sorted_in_b ? d.val_b : d.val_a) + vx_slice(d, f);
+    const int M = g.M, t0 = blockIdx.x * VP_TILE;                        /* M = 0 when process() stopped before the voxel filter */
+    if (tid < 5) cnt[tid] = 0;
+    if (t0 >= M) {                                                       /* the list scatter still reads this block's counts */
+        __syncthreads();
+        if (tid < 5) d.blk[((size_t)f * d.nblk + blockIdx.x) * 5 + tid] = 0;
+        return;
+    }
+    const unsigned *K = reinterpret_cast<const unsigned *>(g.sorted_in_b ? d.key_b : d.key_a) + vx_slice(d, f);
+    const unsigned *V = (g.sorted_in_b ? d.val_b : d.val_a) + vx_slice(d, f);
     const float4 *P = d.xyzw + base;
+    const int nst = min(M - t0, VP_TILE + VP_OV);
+    {
+        unsigned vv[VP_PE + 1], kq[VP_PE + 1];
+#pragma unroll
+        for (int k = 0; k <= VP_PE; ++k) { const int q = tid + k * VP_T; vv[k] = 0u; kq[k] = 0u; if (q < nst) { vv[k] = V[t0 + q]; kq[k] = K[t0 + q]; } }
+#pragma unroll
+        for (int k = 0; k <= VP_PE; ++k) {
+            const int q = tid + k * VP_T;
+            if (q < nst) { float4 pw = P[vv[k]]; pw.w = __uint_as_float(vv[k]); pt[q] = pw; pk[q + 1] = kq[k]; }
+        }
+        if (tid == 0) pk[0] = t0 > 0 ? K[t0 - 1] : 0u;
+    }
+    __syncthreads();
+    /* run heads of the tile, in order; a position that is no head gets its (empty) record here */
+    int hcnt = 0;
+    bool hd[VP_PE];
+#pragma unroll
+    for (int k = 0; k < VP_PE; ++k) {
+        const int q = tid * VP_PE + k, j = t0 + q;
+        hd[k] = j < M && (j == 0 || pk[q] != pk[q + 1]);
+        hcnt += hd[k] ? 1 : 0;
+        if (j < M && !hd[k]) { d.rep[base + j] = -1; d.code[base + j] = 0; }
+    }
+    int nh, hp;
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        int inc = hcnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        int add = 0, all = 0;
+        for (int w = 0; w < VP_T / 32; ++w) { const int x = wsum[w]; if (w < wid) add += x; all += x; }
+        hp = add + inc - hcnt; nh = all;
+    }
+#pragma unroll
+    for (int k = 0; k < VP_PE; ++k) if (hd[k]) heads[hp++] = (unsigned short)(tid * VP_PE + k);
+    __syncthreads();
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-    for (int q = 0; q < 4; ++q) {
-        const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
-        if (j >= M) break;
-        unsigned char code = 0; int rep = -1;
-        const unsigned key = keys[j];
-        if (j == 0 || keys[j - 1] != key) {
-            float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
-            for (int t = j; t < M && keys[t] == key; ++t) { const float4 pw = P[vals[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
-            const float fn = (float)n;
-            const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
-            float best = FLT_MAX;
-            for (int t = j; t < j + n; ++t) {
-                const unsigned p = vals[t];
-                const float4 pw = P[p];
-                const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
-                const float dis = dx * dx + dy * dy + dz * dz;
-                if (best > dis) { best = dis; rep = (int)p; }
-            }
-            code = SPC_HEAD; ++c0;
-            const float4 nw = d.nrm[base + rep];
-            const float nx = nw.x, ny = nw.y, nz = nw.z;
-            if (sp_finite3(nx, ny, nz)) {
-                code |= SPC_NONAN; ++c1;
-                const float4 pw = P[rep];
-                const float px = pw.x, py = pw.y, pz = pw.z;
-                if (px * px + py * py + pz * pz > d.c.noleg_th2) {
-                    code |= SPC_NOLEG; ++c2;
-                    if (nx >= d.c.h_ge || nx <= d.c.h_le) { code |= SPC_H; ++c3; }
-                    else if (nx >= d.c.v_lo && nx <= d.c.v_hi) { code |= SPC_V; ++c4; }
-                }
+    for (int u = tid; u < nh; u += VP_T) {
+        const int q0 = heads[u];
+        const unsigned key = pk[q0 + 1];
+        float sx = 0.f, sy = 0.f, sz = 0.f; int n = 0;
+        int q = q0;
+        for (; q < nst && pk[q + 1] == key; ++q) { const float4 pw = pt[q]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }
+        if (q == nst) for (int t = t0 + q; t < M && K[t] == key; ++t) { const float4 pw = P[V[t]]; sx += pw.x; sy += pw.y; sz += pw.z; ++n; }   /* a run past the staged part */
+        const float fn = (float)n;
+        const float cx = sx / fn, cy = sy / fn, cz = sz / fn;
+        float best = FLT_MAX;
+        float4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = 0; e < n; ++e) {
+            float4 pw;
+            if (q0 + e < nst) pw = pt[q0 + e];
+            else { const unsigned pp = V[t0 + q0 + e]; pw = P[pp]; pw.w = __uint_as_float(pp); }
+            const float dx = cx - pw.x, dy = cy - pw.y, dz = cz - pw.z;
+            const float dis = dx * dx + dy * dy + dz * dz;
+            if (best > dis) { best = dis; rp = pw; }
+        }
+        const int rep = (int)__float_as_uint(rp.w);
+        unsigned char code = SPC_HEAD; ++c0;
+        const float4 nw = d.nrm[base + rep];
+        const float nx = nw.x, ny = nw.y, nz = nw.z;
+        if (sp_finite3(nx, ny, nz)) {
+            code |= SPC_NONAN; ++c1;
+            if (rp.x * rp.x + rp.y * rp.y + rp.z * rp.z > d.c.noleg_th2) {
+                code |= SPC_NOLEG; ++c2;
+                if (nx >= d.c.h_ge || nx <= d.c.h_le) { code |= SPC_H; ++c3; }
+                else if (nx >= d.c.v_lo && nx <= d.c.v_hi) { code |= SPC_V; ++c4; }
             }
         }
-        d.rep[base + j] = rep; d.code[base + j] = code;                       /* positions past M are never read */
+        d.rep[base + t0 + q0] = rep; d.code[base + t0 + q0] = code;
     }
     c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
     c3 = __reduce_add_sync(0xffffffffu, c3); c4 = __reduce_add_sync(0xffffffffu, c4);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); atomicAdd(&cnt[2], c2); atomicAdd(&cnt[3], c3); atomicAdd(&cnt[4], c4); }
+    if ((tid & 31) == 0) { atomicAdd(&cnt[0], c0); atomicAdd(&cnt[1], c1); atomicAdd(&cnt[2], c2); atomicAdd(&cnt[3], c3); atomicAdd(&cnt[4], c4); }
     __syncthreads();
-    if (threadIdx.x < 5) d.blk[((size_t)f * d.nblk + blockIdx.x) * 5 + threadIdx.x] = cnt[threadIdx.x];
+    if (tid < 5) d.blk[((size_t)f * d.nblk + blockIdx.x) * 5 + tid] = cnt[tid];
 }
 
 /* exclusive scan of the per-block counts of one frame (one CTA per frame) + frame totals */
