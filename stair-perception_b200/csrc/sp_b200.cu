@@ -300,7 +300,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
     }
     if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[2], st));
     const bool want_seg = all && show_mode >= SP_SHOW_SEG_HORIZONTAL_PLANE;
-    const int seg_gx = std::max(SEG_GRID_X, std::min(592, N / 8192));     /* CTAs per segment: big single clouds need more */
+    const int seg_gx = std::max(SEG_GRID_X, std::min(592, std::max(N / 8192, 1184 / (2 * nB))));   /* CTAs per segment: big single clouds and small batches need more */
     if (want_seg) {
         CK(cudaMemsetAsync(d.ccnt, 0, sizeof(int) * ((size_t)2 * nB << SP_HASH_BITS), st));
         mark(ctx, "memset_ccnt");

@@ -131,9 +131,13 @@ __global__ void k_knn_refine(SpKnnGrid *grid, int k, int nB)
     grid[f] = g;
 }
 
+/* cell of a point: a multiplication by 1 / h instead of a division (the division cost 15 % of k_knn_normals' instructions).  The
+ * grid only prunes the search: any partition works as long as binning, query and candidate check agree, and the 0.999 slack of the
+ * reach test below covers the rounding of the product at a cell boundary */
 __device__ __forceinline__ void sp_knn_cell(float x, float y, float z, float h, int &a, int &b, int &c)
 {
-    a = (int)floorf(x / h); b = (int)floorf(y / h); c = (int)floorf(z / h);
+    const float ih = 1.0f / h;
+    a = (int)floorf(x * ih); b = (int)floorf(y * ih); c = (int)floorf(z * ih);
 }
 __device__ __forceinline__ unsigned sp_knn_bucket(int a, int b, int c) { return sp_cell_hash(a, b, c) & ((1u << KNN_BITS) - 1u); }
 
@@ -203,8 +207,34 @@ __device__ __forceinline__ void knn_merge128(unsigned long long *L, const unsign
 struct KnnWarp {
     unsigned long long L[KNN_CAP], B[KNN_CAP];
     float gx[KNN_CAP], gy[KNN_CAP], gz[KNN_CAP];
-    float accu[9];
+    float pend[32][10];                  /* queries waiting for their eigen-solve: the nine sums + the neighbour count */
+    float4 pq[32];                       /*                                        the query point {x, y, z, point index} */
 };
+
+/* solvePlaneParameters + flipNormalTowardsViewpoint for the pending queries of a warp, one per lane: pcl::eigen33 is a long scalar
+ * routine (double-precision series), run for one query at a time it kept one lane of the warp busy for a sixth of the kernel */
+__device__ __forceinline__ void knn_solve_pending(SpDev &d, KnnWarp &W, size_t base, int npend, int lane)
+{
+    __syncwarp();
+    if (lane < npend) {
+        const float fc = W.pend[lane][9];
+        const float4 q = W.pq[lane];
+        float ac[9];
+        for (int i = 0; i < 9; ++i) ac[i] = W.pend[lane][i] / fc;
+        float cov[9];
+        cov[0] = ac[0] - ac[6] * ac[6]; cov[1] = ac[1] - ac[6] * ac[7]; cov[2] = ac[2] - ac[6] * ac[8];
+        cov[4] = ac[3] - ac[7] * ac[7]; cov[5] = ac[4] - ac[7] * ac[8]; cov[8] = ac[5] - ac[8] * ac[8];
+        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+        float ev, evec[3];
+        det_eigen33f<0>(cov, &ev, evec);
+        float fx = evec[0], fy = evec[1], fz = evec[2];
+        const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
+        const float cs = (vx * fx + vy * fy + vz * fz);
+        if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
+        d.nrm[base + __float_as_int(q.w)] = make_float4(fx, fy, fz, 0.f);
+    }
+    __syncwarp();
+}
 
 __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, const SpKnnGrid *grid, const int *bstart, const int *bend,
                                                                 const float4 *kpts, int k)
@@ -221,6 +251,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
     const unsigned long long INF = 0xFFFFFFFFFFFFFFFFull;
     const int want = min(min(k, KNN_CAP), g.nvalid);
     const float h = g.h;
+    int npend = 0;                                                      /* queries of this warp waiting for their eigen-solve (warp-uniform) */
     for (int t = blockIdx.x * KNN_WARPS + wid; t < g.nvalid; t += gridDim.x * KNN_WARPS) {
         const float4 q = P[t];
         const int qi = __float_as_int(q.w);
@@ -347,32 +378,22 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
         __syncwarp();
         /* computeMeanAndCovarianceMatrix: nine float sums in neighbour order, lane q owns accumulator q */
         if (lane < 9) {
+            /* accumulators xx xy xz yy yz zz x y z: the two factors of lane q are chosen once, outside the serial loop */
+            const float *pu = lane < 3 ? W.gx : (lane < 5 ? W.gy : (lane == 5 ? W.gz : (lane == 6 ? W.gx : (lane == 7 ? W.gy : W.gz))));
+            const float *pv = lane == 0 ? W.gx : ((lane == 1 || lane == 3) ? W.gy : W.gz);
+            const bool plain = lane >= 6;                               /* sums of x, y, z: factor 1.0f (exact) */
             float acc = 0.f;
             for (int i = 0; i < cnt; ++i) {
-                const float px = W.gx[i], py = W.gy[i], pz = W.gz[i];
-                const float u = lane < 3 ? px : (lane < 5 ? py : (lane == 5 ? pz : (lane == 6 ? px : (lane == 7 ? py : pz))));
-                const float v = lane == 0 ? px : (lane == 1 || lane == 3) ? py : (lane == 2 || lane == 4 || lane == 5) ? pz : 1.0f;
+                const float u = pu[i], v = plain ? 1.0f : pv[i];
                 acc += u * v;
             }
-            W.accu[lane] = acc;
+            if (cnt > 0) W.pend[npend][lane] = acc;
         }
-        __syncwarp();
-        if (lane == 0 && cnt > 0) {
-            const float fc = (float)cnt;
-            float ac[9];
-            for (int i = 0; i < 9; ++i) ac[i] = W.accu[i] / fc;
-            float cov[9];
-            cov[0] = ac[0] - ac[6] * ac[6]; cov[1] = ac[1] - ac[6] * ac[7]; cov[2] = ac[2] - ac[6] * ac[8];
-            cov[4] = ac[3] - ac[7] * ac[7]; cov[5] = ac[4] - ac[7] * ac[8]; cov[8] = ac[5] - ac[8] * ac[8];
-            cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
-            float ev, evec[3];
-            det_eigen33f<0>(cov, &ev, evec);
-            float fx = evec[0], fy = evec[1], fz = evec[2];
-            const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
-            const float cs = (vx * fx + vy * fy + vz * fz);
-            if (cs < 0) { fx *= -1; fy *= -1; fz *= -1; }
-            d.nrm[base + qi] = make_float4(fx, fy, fz, 0.f);
+        if (cnt > 0) {                                                  /* warp-uniform */
+            if (lane == 9) { W.pend[npend][9] = (float)cnt; W.pq[npend] = make_float4(q.x, q.y, q.z, __int_as_float(qi)); }
+            if (++npend == 32) { knn_solve_pending(d, W, base, npend, lane); npend = 0; }
         }
         __syncwarp();
     }
+    if (npend) knn_solve_pending(d, W, base, npend, lane);
 }
