@@ -296,8 +296,14 @@ def bench_latency_b1(sp, dev, recs, Rs):
             ctx.process_frames(rec, R)
             ctx.stair_model(0)
             t1.append((time.perf_counter() - t0) * 1e3)
+        t2 = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            ctx.process_frames(rec, R)
+            ctx.stair_model_batch(0, 1, nthreads=1)
+            t2.append((time.perf_counter() - t0) * 1e3)
         out[name] = {"ms_median": float(np.median(ts)), "ms_min": float(np.min(ts)), "ms_with_stair_model_median": float(np.median(t1)),
-                     "n_planes": int(r[0]["n_planes"])}
+                     "ms_with_packed_stair_model_median": float(np.median(t2)), "n_planes": int(r[0]["n_planes"])}
     ctx.close()
     return out
 
@@ -538,6 +544,26 @@ def main():
                                      "note": "%d distinct scenes entering as uint16 depth + registered colour (6 B/pixel) through sp_process_depth_frames, "
                                              "sharded like the batch, fixed-size records to the host, no exchange" % nd}
         del h_depth, h_bgrx
+        # the consumer on the measured path: chunk by chunk, the front-end on device-resident clouds, then the batched stair model
+        # (sp_stair_model_batch: one pack kernel + one copy of the chunk's plane clouds, host model on the box's cores)
+        nsm = min(args.max_batch, Fl)
+        res_sm = np.zeros(nsm, dtype=sp.FRAME_DTYPE)
+        ctx_sm = sp.Context(device=local, width=W, height=H, max_batch=nsm)
+
+        def step_stair():
+            for c0 in range(0, 4 * nsm, nsm):
+                o = (c0 % max(nsm, Fl - nsm + 1))
+                ctx_sm.process_frames(d_all_or_mine[o:o + nsm], d_R_all_or_mine[o:o + nsm], device_input=True, nframes=nsm, results=res_sm)
+                last["stairs"] = ctx_sm.stair_model_batch(0, nsm)
+
+        d_all_or_mine, d_R_all_or_mine = (d_clouds, d_R) if world == 1 else (base.index_select(0, (torch.arange(lo, hi, device=dev) % N_DISTINCT)), base_R.index_select(0, (torch.arange(lo, hi, device=dev) % N_DISTINCT)))
+        step_stair()
+        ms_s = timed(step_stair, 2)
+        extras["e2e_with_stair_model"] = {"value": 4 * nsm * world * 2 / (ms_s / 1e3), "unit": "frames/s", "frames_per_chunk": nsm, "ms_per_chunk": ms_s / 8,
+                                          "stairs_found": int(last["stairs"]["has_stair"].sum()), "host_threads": host_cores(),
+                                          "note": "one chunk at a time: front-end on device-resident clouds, records to the host, then sp_stair_model_batch "
+                                                  "(StairDetection::stairModel for every frame of the chunk); no overlap between the chunk's kernels and the host model"}
+        ctx_sm.close()
         if rank == 0 and world == 1:
             extras["config4"] = bench_config4(sp, dev, peak)
             extras["latency_b1"] = bench_latency_b1(sp, dev, recs, Rs)

@@ -222,6 +222,11 @@ typedef struct sp_stair {
     float virtual_contour[SP_MAX_VIRTUAL_PLANES][4][3];      /* virtual riser k (plane index -2 - k) */
 } sp_stair;
 int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out);
+/* The same consumer for many frames at once -- frames [first_frame, first_frame + nframes) of the last chunk: the plane clouds of
+ * all of them are packed by one kernel and cross PCIe in one copy (with the records and the per-frame offsets: three copies per
+ * chunk instead of several blocking ones per findMinMaxProjPoint call), then the host model runs one frame per task on
+ * `nthreads` host threads (0 = all).  out[i] is bit-identical to sp_stair_model(ctx, first_frame + i, ...). */
+int sp_stair_model_batch(sp_ctx *ctx, int first_frame, int nframes, sp_stair *out, int nthreads);
 
 /* The step AFTER the path (host-side, no device work): the driver's hold-last-good filter and the 19-byte robot packet.
  * sp_result_def = ResultDef (/root/reference/include/common.h:133-141).  sp_resolve_result replaces DProcessor::resolve_result

@@ -290,6 +290,17 @@ class Context:
         self._check(L.sp_stair_model(self.h, frame, out.ctypes.data), "sp_stair_model")
         return out[0]
 
+    def stair_model_batch(self, first_frame=0, nframes=None, nthreads=0):
+        """sp_stair_model for frames [first_frame, first_frame + nframes) of the last chunk: one pack kernel, three copies, the
+        host model on `nthreads` threads.  Returns a STAIR_DTYPE array."""
+        if nframes is None:
+            nframes = self.max_batch - first_frame
+        out = np.zeros(nframes, dtype=STAIR_DTYPE)
+        L = self.L
+        L.sp_stair_model_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self._check(L.sp_stair_model_batch(self.h, first_frame, nframes, out.ctypes.data, nthreads), "sp_stair_model_batch")
+        return out
+
     def stage_ms(self):
         arr = (C.c_float * 16)()
         n = self.L.sp_stage_ms(self.h, arr, 16)

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <random>
 #include <string>
 #include <vector>
@@ -151,6 +152,7 @@ struct sp_ctx {
     sp_frame_result *d_batch_res = nullptr;   /* records of a whole batch on the device (compact entry point), grown on demand */
     size_t batch_res_cap = 0;
     long long *d_coff = nullptr; size_t coff_cap = 0;
+    float *d_cloud = nullptr, *h_cloud = nullptr; size_t cloud_cap = 0;   /* packed plane clouds of a chunk (batched stair model), points */
     int64_t launches = 0;
     std::string err;
     std::mutex mu;
@@ -494,6 +496,8 @@ void sp_destroy(sp_ctx *ctx)
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->d_batch_res) cudaFree(ctx->d_batch_res);
     if (ctx->d_coff) cudaFree(ctx->d_coff);
+    if (ctx->d_cloud) cudaFree(ctx->d_cloud);
+    if (ctx->h_cloud) cudaFreeHost(ctx->h_cloud);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     for (int i = 0; i <= STG_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
@@ -1134,6 +1138,96 @@ int sp_stair_model(sp_ctx *ctx, int frame, sp_stair *out)
     CK(cudaMemcpy(fr.data(), ctx->last_res + frame, sizeof(sp_frame_result), cudaMemcpyDeviceToHost));
     DevicePoints pts; pts.ctx = ctx; pts.frame = frame; pts.fr = fr.data();
     sp_stairmodel::stair_model(ctx->params, fr[0], pts, out);
+    return SP_OK;
+}
+
+namespace {
+/* point access for the batched stair model: the chunk's plane clouds were packed on the device and copied once */
+struct HostPoints : sp_stairmodel::StairPoints {
+    const sp_frame_result *fr; const float *xyz;               /* this frame's record and its packed plane clouds */
+    bool gather(int plane, std::vector<float> &out) override
+    {
+        if (plane < 0 || plane >= fr->n_planes) return false;
+        const sp_plane_record &pr = fr->planes[plane];
+        out.insert(out.end(), xyz + 3 * (size_t)pr.first, xyz + 3 * ((size_t)pr.first + (size_t)pr.count));
+        return true;
+    }
+    bool minmax(int plane, const float *c, const float *dir, float *max_xyz, float *min_xyz) override
+    {
+        if (plane < 0 || plane >= fr->n_planes || fr->planes[plane].count <= 0) return false;
+        const sp_plane_record &pr = fr->planes[plane];
+        const float *p = xyz + 3 * (size_t)pr.first;
+        /* findMinMaxProjPoint (StairPerception.cpp:2780-2808), the arithmetic of k_minmax_proj: strict compares, first occurrence */
+        float bmx = -FLT_MAX, bmn = FLT_MAX; int amx = -1, amn = -1;
+        for (int i = 0; i < pr.count; ++i) {
+            const float px = p[3 * i] - c[0], py = p[3 * i + 1] - c[1], pz = p[3 * i + 2] - c[2];
+            const float proj = dir[0] * px + (dir[1] * py + dir[2] * pz);
+            if (proj > bmx) { bmx = proj; amx = i; }
+            if (proj < bmn) { bmn = proj; amn = i; }
+        }
+        if (amx < 0 || amn < 0) return false;
+        for (int k = 0; k < 3; ++k) { max_xyz[k] = p[3 * amx + k]; min_xyz[k] = p[3 * amn + k]; }
+        return true;
+    }
+};
+} // namespace
+
+int sp_stair_model_batch(sp_ctx *ctx, int first_frame, int nframes, sp_stair *out, int nthreads)
+{
+    if (!ctx) return SP_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    sp_ctx *own = ctx;
+    ctx = lane_of_last_chunk(ctx);
+    if (!out || first_frame < 0 || nframes < 0 || first_frame + nframes > ctx->last_nB) { ERR(ctx) = "bad argument"; return SP_ERR_ARG; }
+    if (nframes == 0) return SP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const sp_frame_result *dres = ctx->last_res + first_frame;
+    SpDev d = ctx->d;
+    d.xyzw += (size_t)first_frame * ctx->N; d.plane_idx += (size_t)first_frame * ctx->N;
+    /* one scan, one pack kernel, three copies for the whole chunk: offsets, records, packed clouds */
+    if ((size_t)nframes + 1 > ctx->coff_cap) {
+        if (ctx->d_coff) cudaFree(ctx->d_coff);
+        ctx->d_coff = nullptr; ctx->coff_cap = 0;
+        CK(cudaMalloc((void **)&ctx->d_coff, sizeof(long long) * ((size_t)nframes + 1)));
+        ctx->coff_cap = (size_t)nframes + 1;
+    }
+    k_plane_cloud_offsets<<<1, 1024, 0, ctx->stream>>>(dres, nframes, ctx->d_coff);
+    std::vector<long long> off((size_t)nframes + 1);
+    std::vector<sp_frame_result> fr((size_t)nframes);
+    CK(cudaMemcpyAsync(off.data(), ctx->d_coff, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(fr.data(), dres, sizeof(sp_frame_result) * (size_t)nframes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const long long total = off[(size_t)nframes];
+    if ((size_t)total > ctx->cloud_cap) {
+        if (ctx->d_cloud) cudaFree(ctx->d_cloud);
+        if (ctx->h_cloud) cudaFreeHost(ctx->h_cloud);
+        ctx->d_cloud = nullptr; ctx->h_cloud = nullptr; ctx->cloud_cap = 0;
+        const size_t cap = (size_t)total + (size_t)total / 4 + 1024;
+        CK(cudaMalloc((void **)&ctx->d_cloud, cap * 12));
+        CK(cudaMallocHost((void **)&ctx->h_cloud, cap * 12));
+        ctx->cloud_cap = cap;
+    }
+    if (total > 0) {
+        k_plane_cloud_pack<<<dim3(8, nframes), 256, 0, ctx->stream>>>(d, dres, ctx->d_coff, ctx->d_cloud, (long long)ctx->cloud_cap);
+        CK(cudaMemcpyAsync(ctx->h_cloud, ctx->d_cloud, (size_t)total * 12, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->launches += 2;
+    /* the host model, like the reference's (a few tens of planes per frame), one frame per task */
+    const int nt = std::max(1, std::min(nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency(), std::min(nframes, 64)));
+    const sp_params params = own->params;
+    auto work = [&](int t) {
+        for (int f = t; f < nframes; f += nt) {
+            HostPoints pts; pts.fr = &fr[(size_t)f]; pts.xyz = ctx->h_cloud + 3 * off[(size_t)f];
+            sp_stairmodel::stair_model(params, fr[(size_t)f], pts, out + f);
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
     return SP_OK;
 }
 

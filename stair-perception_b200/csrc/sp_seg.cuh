@@ -1101,3 +1101,43 @@ __global__ void __launch_bounds__(128) k_compact_copy(const sp_frame_result *res
     int *dst = reinterpret_cast<int *>(out + off[f]);
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
 }
+
+/* ==================================================================================================== */
+/* The consumer's view of a chunk: the point clouds of every hand-off plane of every frame, packed {x, y, z} in the reference's
+ * point order, frames back to back (what StairDetection::stairModel reads through Plane::cloud, StairPerception.cpp:1621-2773) */
+__global__ void __launch_bounds__(1024) k_plane_cloud_offsets(const sp_frame_result *res, int nframes, long long *off)
+{
+    __shared__ long long ws[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int f0 = 0; f0 < nframes; f0 += 1024) {
+        const int f = f0 + threadIdx.x;
+        const long long v = f < nframes ? (long long)res[f].n_plane_points : 0;
+        long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) ws[wid] = inc;
+        __syncthreads();
+        long long add = carry;
+        for (int w = 0; w < wid; ++w) add += ws[w];
+        if (f < nframes) off[f] = add + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = add + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[nframes] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_plane_cloud_pack(SpDev d, const sp_frame_result *res, const long long *off, float *out, long long cap_points)
+{
+    const int f = blockIdx.y;
+    const int n = res[f].n_plane_points;
+    if (off[f] + n > cap_points) return;
+    const size_t base = (size_t)f * d.N;
+    float *o = out + 3 * off[f];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 pw = d.xyzw[base + d.plane_idx[base + i]];
+        o[3 * i] = pw.x; o[3 * i + 1] = pw.y; o[3 * i + 2] = pw.z;
+    }
+}

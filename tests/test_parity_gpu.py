@@ -468,3 +468,24 @@ def test_product_against_the_oracles_independent_numerics(sp, orc, samples, synt
             assert np.abs(q["coef"] - sg * q2["coef"]).max() < 1e-4
             assert np.abs(q["center"] - q2["center"]).max() < 1e-6
             assert np.allclose(q["eval"], q2["eval"], rtol=1e-3, atol=1e-9)
+
+
+def test_batched_stair_model_equals_per_frame_model(sp, synth, samples):
+    """sp_stair_model_batch: the plane clouds of a whole chunk packed by one kernel and copied once, the host model on several
+    threads -- record for record what sp_stair_model returns frame by frame (which pulls points per findMinMaxProjPoint call)"""
+    frames = [synth.make_frame(f) for f in (0, 3, 7, 12)]
+    recs = [samples["0001"][0], samples["0000"][0]] + [f[0] for f in frames]
+    Rs = [np.eye(3, dtype=np.float32).reshape(9)] * 2 + [f[1] for f in frames]
+    recs.append(recs[2].copy())
+    recs[-1]["rgba"] = 0                                      # an empty frame: no planes, no stair
+    Rs.append(Rs[2])
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=len(recs))
+    res = ctx.process_frames(np.stack(recs), np.stack(Rs))
+    one = np.stack([ctx.stair_model(i) for i in range(len(recs))])
+    for nthreads in (1, 4):
+        many = ctx.stair_model_batch(0, len(recs), nthreads=nthreads)
+        assert many.tobytes() == one.tobytes()
+    part = ctx.stair_model_batch(2, 3)
+    assert part.tobytes() == one[2:5].tobytes()
+    assert int(one["has_stair"].sum()) >= 4 and int(one[-1]["has_stair"]) == 0 and int(res[-1]["n_planes"]) == 0
+    ctx.close()
