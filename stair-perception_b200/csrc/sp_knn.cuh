@@ -173,12 +173,13 @@ __global__ void __launch_bounds__(256) k_knn_starts(SpDev d, int *bstart, int *b
 }
 
 /* warp-synchronous bitonic machinery on 128 u64 keys in shared memory */
-__device__ __forceinline__ void knn_sort128(unsigned long long *A, int lane)
+/* ascending sort of the first n keys (n = 32, 64 or 128: a batch of waiting candidates is padded to the next of them, a second
+ * batch of a query is usually half the size of the first); the keys past n must already be INF */
+__device__ __forceinline__ void knn_sort128(unsigned long long *A, int lane, int n = 128)
 {
-    for (int size = 2; size <= 128; size <<= 1)
+    for (int size = 2; size <= n; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int q = lane; q < 64; q += 32) {
+            for (int q = lane; q < (n >> 1); q += 32) {
                 const int i = 2 * q - (q & (stride - 1)), j = i + stride;
                 const bool asc = (i & size) == 0;
                 const unsigned long long a = A[i], b = A[j];
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
                             if (bn > KNN_CAP - 32) {
                                 for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
                                 __syncwarp();
-                                knn_sort128(W.B, lane);
+                                knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
                                 knn_merge128(W.L, W.B, lane);
                                 bn = 0;
                                 thr = want > 0 ? W.L[want - 1] : INF;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
             if (bn) {
                 for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
                 __syncwarp();
-                knn_sort128(W.B, lane);
+                knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
                 knn_merge128(W.L, W.B, lane);
                 bn = 0;
                 thr = want > 0 ? W.L[want - 1] : INF;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
                     if (bn > KNN_CAP - 32) {
                         for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
                         __syncwarp();
-                        knn_sort128(W.B, lane);
+                        knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
                         knn_merge128(W.L, W.B, lane);
                         bn = 0;
                         thr = want > 0 ? W.L[want - 1] : INF;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
             if (bn) {
                 for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
                 __syncwarp();
-                knn_sort128(W.B, lane);
+                knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
                 knn_merge128(W.L, W.B, lane);
                 bn = 0;
             }

@@ -47,6 +47,18 @@ def main():
             if key in hdr:
                 i = hdr.index(key)
                 lines.append("| %s (`%s`) | %s | %s |" % (label, key, r[i], units[i]))
+        # warp-stall breakdown: share of the sampled warp states (smsp__pcsamp_warps_issue_stalled_*), largest first
+        st = []
+        for i, key in enumerate(hdr):
+            if key.startswith("smsp__pcsamp_warps_issue_stalled_") and not key.endswith("_not_issued"):
+                try:
+                    st.append((float(r[i].replace(",", "")), key[len("smsp__pcsamp_warps_issue_stalled_"):]))
+                except ValueError:
+                    pass
+        tot = sum(v for v, _ in st)
+        if tot > 0:
+            lines.append("")
+            lines.append("warp states (pc sampling): " + ", ".join("%s %.1f %%" % (k, 100.0 * v / tot) for v, k in sorted(st, reverse=True)[:8]))
         lines.append("")
     out = "\n".join(lines)
     if len(sys.argv) > 2:
