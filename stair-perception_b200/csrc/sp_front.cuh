@@ -90,6 +90,9 @@ __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e
     const int rr = e / K1_TW, cc = e - rr * K1_TW;
     const int half = K >> 1;
     const int g0 = (rr + 2 - half) * K1_GW + (cc + 2 - half);
+    const size_t gi = tile_base + (size_t)rr * W + cc;
+    const float4 pw = d.xyzw[gi];                       /* the point itself, for the flip (written by this CTA a barrier ago): requested
+                                                           before the sums so that its latency hides behind them */
     double sgx0 = 0.0, sgx1 = 0.0, sgx2 = 0.0, sgy0 = 0.0, sgy1 = 0.0, sgy2 = 0.0;
 #pragma unroll
     for (int a = 0; a < K; ++a) {
@@ -103,8 +106,6 @@ __device__ __forceinline__ void k1_normal(const K1Smem &s, const SpDev &d, int e
         }
         sgx0 += rx0; sgx1 += rx1; sgx2 += rx2; sgy0 += ry0; sgy1 += ry1; sgy2 += ry2;
     }
-    const size_t gi = tile_base + (size_t)rr * W + cc;
-    const float4 pw = d.xyzw[gi];                       /* the point itself, for the flip: written by this CTA in S0b, a barrier ago */
     if (FAST) st_finish(d, gi, pw.x, pw.y, pw.z, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
     else k1_finish(d, gi, pw.x, pw.y, pw.z, sgx0, sgx1, sgx2, sgy0, sgy1, sgy2);
 }
@@ -368,6 +369,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
         }
         for (int i = p0 + tid; i < p1; i += K1_THREADS) {
             const int e = s.list[i], rr = e / K1_TW, cc = e - rr * K1_TW;
+            const size_t gi = tile_base + (size_t)rr * W + cc;
+            const float4 pw = d.xyzw[gi];
             const double *c = csum + (rr - b0) * K1_GW + cc;
             double sg[6];
 #pragma unroll
@@ -375,8 +378,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals(SpDev d)
                 const double *q = c + k * rows * K1_GW;
                 sg[k] = q[0] + q[1] + q[2] + q[3] + q[4];
             }
-            const size_t gi = tile_base + (size_t)rr * W + cc;
-            const float4 pw = d.xyzw[gi];
             k1_finish(d, gi, pw.x, pw.y, pw.z, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
         }
         if (b0 == 0) {
@@ -621,6 +622,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals_tma(SpDev d, c
         }
         for (int i = p0 + tid; i < p1; i += K1_THREADS) {
             const int e = s.list[i], rr = e / K1_TW, cc = e - rr * K1_TW;
+            const size_t gi = tile_base + (size_t)rr * W + cc;
+            const float4 pw = d.xyzw[gi];
             const double *c = csum + (rr - b0) * K1_GW + cc;
             double sg[6];
 #pragma unroll
@@ -628,8 +631,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k_ingest_normals_tma(SpDev d, c
                 const double *q = c + k * rows * K1_GW;
                 sg[k] = q[0] + q[1] + q[2] + q[3] + q[4];
             }
-            const size_t gi = tile_base + (size_t)rr * W + cc;
-            const float4 pw = d.xyzw[gi];
             st_finish(d, gi, pw.x, pw.y, pw.z, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]);
         }
         if (b0 == 0) {

@@ -53,6 +53,9 @@ def gather_results(local, nframes, group=None, device=None):
     return np.concatenate(parts)
 
 
+_slots = {}                                                      # the receive buffer of the last gather, reused while the size stays
+
+
 def gather_compact(local, nbytes, group=None, host_out=None):
     """All-gather of COMPACT records (sp_process_frames_compact: 64-byte header + n_planes plane records per frame) straight
     from device memory: no host bounce, about 3 KB per frame on the wire instead of the 14 400-byte fixed record.
@@ -78,9 +81,16 @@ def gather_compact(local, nbytes, group=None, host_out=None):
     pad = (max(sizes) + 15) // 16 * 16                          # equal-sized slots: one fixed-size collective
     if local.numel() < pad:
         raise ValueError("compact buffer of %d bytes cannot hold the largest shard (%d bytes)" % (local.numel(), pad))
-    slots = torch.empty(world * pad, dtype=torch.uint8, device=local.device)
+    key = (str(local.device), world * pad)
+    slots = _slots.get(key)
+    if slots is None:
+        _slots.clear()
+        slots = _slots[key] = torch.empty(world * pad, dtype=torch.uint8, device=local.device)
     dist.all_gather_into_tensor(slots, local[:pad], group=group)
-    packed = torch.cat([slots[r * pad: r * pad + sizes[r]] for r in range(world)])
+    if all(sz == pad for sz in sizes):                          # records are multiples of 16 bytes: equal shards leave no gaps
+        packed = slots
+    else:
+        packed = torch.cat([slots[r * pad: r * pad + sizes[r]] for r in range(world)])
     total = int(packed.numel())
     if host_out is not None and packed.is_cuda:
         host_out[:total].copy_(packed, non_blocking=True)
