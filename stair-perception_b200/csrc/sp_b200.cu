@@ -342,7 +342,7 @@ int run_chunk(sp_ctx *ctx, const float4 *d_in, const float *d_R, int nB, int sho
                 ctx->launches += 1;
             }
         }
-        k_finalize<<<(nB + 63) / 64, 64, 0, st>>>(d, nB, ctx->d_order, (want_seg && show_mode >= SP_SHOW_STAIR) ? 1 : 0, show_mode);
+        k_finalize<<<nB, 64, 0, st>>>(d, nB, ctx->d_order, (want_seg && show_mode >= SP_SHOW_STAIR) ? 1 : 0, show_mode);
         mark(ctx, "k_finalize");
         k_gather_plane_points<<<dim3(SP_MAX_PLANES, nB), 256, 0, st>>>(d, ctx->d_order);
         mark(ctx, "k_gather_plane_points");

@@ -962,47 +962,57 @@ __global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
 
 /* sortPlanesByXValues (StairPerception.cpp:1383-1441) + the per-frame result record; one thread per frame.
  * order[f][i] = (segment-local merged plane index) | hv << 16 is kept for the plane point gather. */
-__global__ void k_finalize(SpDev d, int nB, int *order, int with_planes, int show_mode)
+__global__ void __launch_bounds__(64) k_finalize(SpDev d, int nB, int *order, int with_planes, int show_mode)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    /* one CTA per frame: thread 0 replays the selection by centre.x (a few tens of planes), all threads copy the records */
+    __shared__ int s_src[SP_MAX_PLANES], s_first[SP_MAX_PLANES], s_np, s_total;
+    const int f = blockIdx.x;
     if (f >= nB) return;
     sp_frame_result &R = d.results[f];
-    const int *c = d.counts + f * SP_NCOUNT;
-    R.status = c[0] | (d.flags[f] ? (0x100 | (d.flags[f] << 9)) : 0);
-    R.n_valid = c[1]; R.n_crop = c[2]; R.n_voxel = c[3]; R.n_nonan = c[4]; R.n_noleg = c[5]; R.n_h = c[6]; R.n_v = c[7];
-    R.n_clusters_h = d.n_clusters[2 * f]; R.n_clusters_v = d.n_clusters[2 * f + 1];
-    R.n_seg_h = d.n_seg[2 * f]; R.n_seg_v = d.n_seg[2 * f + 1];
-    int nh = d.n_merged[2 * f], nv = d.n_merged[2 * f + 1];
-    R.n_planes_h = nh; R.n_planes_v = nv;
-    /* process() returns at the ShowModeDef tap (StairPerception.cpp:49-176): nothing computed past it is reported, even
-     * where a fused kernel happened to produce it (H and V sets are classified, clustered and segmented together) */
-    if (show_mode < SP_SHOW_VOXEL) { R.n_voxel = 0; R.n_nonan = 0; }
-    if (show_mode < SP_SHOW_NOLEG) R.n_noleg = 0;
-    if (show_mode < SP_SHOW_HORIZONTAL_CLOUD) { R.n_h = 0; R.n_v = 0; }
-    if (show_mode < SP_SHOW_SEG_HORIZONTAL_PLANE) { R.n_clusters_h = 0; R.n_seg_h = 0; }
-    if (show_mode < SP_SHOW_SEG_VERTICAL_PLANE) { R.n_clusters_v = 0; R.n_seg_v = 0; }
-    if (show_mode < SP_SHOW_MERGE_HORIZONTAL_PLANE) R.n_planes_h = 0;
-    if (show_mode < SP_SHOW_MERGE_VERTICAL_PLANE) R.n_planes_v = 0;
-    if (!with_planes) { nh = 0; nv = 0; }
-    float chx[SP_PSEG], cvx[SP_PSEG];
-    for (int i = 0; i < nh; ++i) chx[i] = d.info[(2 * f) * SP_PSEG + i].center[0];
-    for (int i = 0; i < nv; ++i) cvx[i] = d.info[(2 * f + 1) * SP_PSEG + i].center[0];
-    int total = nh + nv, np = 0, first = 0;
-    if (total > SP_MAX_PLANES) { total = SP_MAX_PLANES; R.status |= 0x100 | (8 << 9); }
-    for (int i = 0; i < total; ++i) {
-        float xmax = -FLT_MAX; int hi = 0, vi = 0; bool in_h = false;
-        for (int h = 0; h < nh; ++h) if (chx[h] > xmax) { xmax = chx[h]; hi = h; in_h = true; }
-        for (int v = 0; v < nv; ++v) if (cvx[v] > xmax) { xmax = cvx[v]; vi = v; in_h = false; }
-        if (!in_h && nv == 0) break;
-        const int s = in_h ? 2 * f : 2 * f + 1, m = in_h ? hi : vi;
-        if (in_h) chx[hi] = -FLT_MAX; else cvx[vi] = -FLT_MAX;
-        sp_plane_record r = d.info[s * SP_PSEG + m];
-        r.first = first; first += r.count;
-        R.planes[np] = r;
-        order[f * SP_MAX_PLANES + np] = m | ((in_h ? 0 : 1) << 16);
-        ++np;
+    if (threadIdx.x == 0) {
+        const int *c = d.counts + f * SP_NCOUNT;
+        R.status = c[0] | (d.flags[f] ? (0x100 | (d.flags[f] << 9)) : 0);
+        R.n_valid = c[1]; R.n_crop = c[2]; R.n_voxel = c[3]; R.n_nonan = c[4]; R.n_noleg = c[5]; R.n_h = c[6]; R.n_v = c[7];
+        R.n_clusters_h = d.n_clusters[2 * f]; R.n_clusters_v = d.n_clusters[2 * f + 1];
+        R.n_seg_h = d.n_seg[2 * f]; R.n_seg_v = d.n_seg[2 * f + 1];
+        int nh = d.n_merged[2 * f], nv = d.n_merged[2 * f + 1];
+        R.n_planes_h = nh; R.n_planes_v = nv;
+        /* process() returns at the ShowModeDef tap (StairPerception.cpp:49-176): nothing computed past it is reported, even
+         * where a fused kernel happened to produce it (H and V sets are classified, clustered and segmented together) */
+        if (show_mode < SP_SHOW_VOXEL) { R.n_voxel = 0; R.n_nonan = 0; }
+        if (show_mode < SP_SHOW_NOLEG) R.n_noleg = 0;
+        if (show_mode < SP_SHOW_HORIZONTAL_CLOUD) { R.n_h = 0; R.n_v = 0; }
+        if (show_mode < SP_SHOW_SEG_HORIZONTAL_PLANE) { R.n_clusters_h = 0; R.n_seg_h = 0; }
+        if (show_mode < SP_SHOW_SEG_VERTICAL_PLANE) { R.n_clusters_v = 0; R.n_seg_v = 0; }
+        if (show_mode < SP_SHOW_MERGE_HORIZONTAL_PLANE) R.n_planes_h = 0;
+        if (show_mode < SP_SHOW_MERGE_VERTICAL_PLANE) R.n_planes_v = 0;
+        if (!with_planes) { nh = 0; nv = 0; }
+        float chx[SP_PSEG], cvx[SP_PSEG];
+        for (int i = 0; i < nh; ++i) chx[i] = d.info[(2 * f) * SP_PSEG + i].center[0];
+        for (int i = 0; i < nv; ++i) cvx[i] = d.info[(2 * f + 1) * SP_PSEG + i].center[0];
+        int total = nh + nv, np = 0, first = 0;
+        if (total > SP_MAX_PLANES) { total = SP_MAX_PLANES; R.status |= 0x100 | (8 << 9); }
+        for (int i = 0; i < total; ++i) {
+            float xmax = -FLT_MAX; int hi = 0, vi = 0; bool in_h = false;
+            for (int h = 0; h < nh; ++h) if (chx[h] > xmax) { xmax = chx[h]; hi = h; in_h = true; }
+            for (int v = 0; v < nv; ++v) if (cvx[v] > xmax) { xmax = cvx[v]; vi = v; in_h = false; }
+            if (!in_h && nv == 0) break;
+            const int s = in_h ? 2 * f : 2 * f + 1, m = in_h ? hi : vi;
+            if (in_h) chx[hi] = -FLT_MAX; else cvx[vi] = -FLT_MAX;
+            s_src[np] = s * SP_PSEG + m; s_first[np] = first;
+            first += d.info[s * SP_PSEG + m].count;
+            order[f * SP_MAX_PLANES + np] = m | ((in_h ? 0 : 1) << 16);
+            ++np;
+        }
+        s_np = np; s_total = first;
+        R.n_planes = np; R.n_plane_points = first;
     }
-    R.n_planes = np; R.n_plane_points = first;
+    __syncthreads();
+    for (int i = threadIdx.x; i < s_np; i += blockDim.x) {
+        sp_plane_record r = d.info[s_src[i]];
+        r.first = s_first[i];
+        R.planes[i] = r;
+    }
 }
 
 /* final plane point lists in the reference's order: one CTA per (plane, frame) */

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(VX_T) k_vx_scan(SpDev d, int p)
 }
 
 /* one tile: stable rank of every key among the tile's keys of the same digit, then the scatter */
-__global__ void __launch_bounds__(VX_T) k_vx_scatter(SpDev d, int p)
+__global__ void __launch_bounds__(VX_T, 3) k_vx_scatter(SpDev d, int p)
 {
     __shared__ unsigned wc[VX_NW][VX_BINS];
     const int f = blockIdx.y, tile = blockIdx.x;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(VX_T) k_vx_scatter(SpDev d, int p)
 #define VP_PE 4
 #define VP_TILE (VP_T * VP_PE)
 #define VP_OV 64
-__global__ void __launch_bounds__(VP_T) k_vx_pick(SpDev d)
+__global__ void __launch_bounds__(VP_T, 6) k_vx_pick(SpDev d)
 {
     __shared__ float4 pt[VP_TILE + VP_OV];                               /* {x, y, z, pixel} in sorted order */
     __shared__ unsigned pk[VP_TILE + VP_OV + 1];                         /* voxel indices; [0] = the key before the tile */
