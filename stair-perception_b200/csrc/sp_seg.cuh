@@ -33,13 +33,19 @@ __global__ void __launch_bounds__(256) k_cl_count(SpDev d)
     const size_t base = (size_t)s * d.N;
     int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
     const float cell = d.c.cell;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = d.pts[base + i];
-        int a, b, c;
-        const unsigned h = sp_point_bucket(p, cell, a, b, c);
-        atomicAdd(&cnt[h], 1);
-        d.parent[base + i] = i;
-        d.csize[base + i] = 0;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        unsigned h = 0x80000000u + lane;                     /* lanes past the end: a group of their own */
+        if (i < n) {
+            const float4 p = d.pts[base + i];
+            int a, b, c;
+            h = sp_point_bucket(p, cell, a, b, c);
+            d.parent[base + i] = i;
+            d.csize[base + i] = 0;
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, h);  /* list neighbours often share a cell: one atomic per cell and warp */
+        if (i < n && lane == __ffs(m) - 1) atomicAdd(&cnt[h], __popc(m));
     }
 }
 
@@ -89,12 +95,26 @@ __global__ void __launch_bounds__(256) k_cl_scatter(SpDev d)
     int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     const float cell = d.c.cell;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = d.pts[base + i];
-        int a, b, c;
-        const unsigned h = sp_point_bucket(p, cell, a, b, c);
-        const int pos = start[h] + atomicSub(&cnt[h], 1) - 1;          /* drains the counters back to zero */
-        d.spts[base + pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        unsigned h = 0x80000000u + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            p = d.pts[base + i];
+            int a, b, c;
+            h = sp_point_bucket(p, cell, a, b, c);
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, h);
+        const int leader = __ffs(m) - 1;
+        int top = 0;
+        if (i < n && lane == leader) top = atomicSub(&cnt[h], __popc(m));   /* drains the counters back to zero */
+        top = __shfl_sync(0xffffffffu, top, leader);
+        if (i < n) {
+            const int pos = start[h] + top - 1 - __popc(m & lt);
+            d.spts[base + pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        }
     }
 }
 
