@@ -428,12 +428,13 @@ static int create_impl(const sp_params *params, int device, int width, int heigh
     DA(d.vcnt, B * d.nblk); DA(d.voff, B * d.nblk); DA(d.vth, B * d.ntile * VX_BINS);
     DA(d.key_a, BN); DA(d.key_b, BN); DA(d.val_a, BN + 4 * B); DA(d.val_b, BN + 4 * B);      /* k_voxel_frame: slices of (N + 3) & ~3 u32 per frame */
     DA(d.rep, BN); DA(d.code, BN); DA(d.blk, B * d.nblk * 5); DA(d.voxel_idx, BN); DA(d.voxel_code, BN);
-    DA(d.pts, S * N); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, S * N);
-    DA(d.parent, S * N); DA(d.root, S * N); DA(d.csize, S * N);
+    /* per-segment point arrays: the two segments of a frame share one slice of N entries (sp_seg_base) */
+    DA(d.pts, BN); DA(d.seg_n, S); DA(d.ccnt, S << SP_HASH_BITS); DA(d.cstart, S * ((1 << SP_HASH_BITS) + 1)); DA(d.spts, BN);
+    DA(d.parent, BN); DA(d.root, BN); DA(d.csize, BN);
     DA(d.n_clusters, S); DA(d.n_cand, S);
     DA(d.cand_root, S * SP_CMAX); DA(d.cand_size, S * SP_CMAX); DA(d.cand_off, S * SP_CMAX); DA(d.cand_slot, S * SP_CMAX);
-    DA(d.wx, S * N); DA(d.wy, S * N); DA(d.wz, S * N); DA(d.wpix, S * N); DA(d.plane_pts, S * N);
-    DA(d.vx, S * N); DA(d.vy, S * N); DA(d.vz, S * N); DA(d.vpix, S * N); DA(d.plane_x, S * N); DA(d.plane_y, S * N); DA(d.plane_z, S * N);
+    DA(d.wx, BN); DA(d.wy, BN); DA(d.wz, BN); DA(d.wpix, BN); DA(d.plane_pts, BN);
+    DA(d.vx, BN); DA(d.vy, BN); DA(d.vz, BN); DA(d.vpix, BN); DA(d.plane_x, BN); DA(d.plane_y, BN); DA(d.plane_z, BN);
     DA(d.seg_planes, S * SP_PSEG); DA(d.logs, S * SP_LOGCAP * 10); DA(d.log_n, S);
     DA(d.n_seg, S); DA(d.chunks, S * SP_PSEG); DA(d.chunk_next, S * SP_PSEG); DA(d.merged, S * SP_PSEG); DA(d.n_merged, S);
     DA(d.info, S * SP_PSEG); DA(d.results, B); DA(d.plane_idx, BN); DA(ctx->d_order, B * SP_MAX_PLANES);
@@ -991,14 +992,16 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
         const size_t s = 2 * f + (isv ? 1 : 0);
         const std::string sub = name.substr(2);
         int n = 0; CK(d2h(&n, d.seg_n + s, 4));
+        int n_h = 0; CK(d2h(&n_h, d.seg_n + 2 * f, 4));
+        const size_t sbase = f * N + (isv ? (size_t)n_h : 0);              /* sp_seg_base: the vertical set follows the horizontal one */
         if (sub == "idx") {
-            std::vector<float4> p(n); CK(d2h(p.data(), d.pts + s * N, (size_t)n * 16));
+            std::vector<float4> p(n); CK(d2h(p.data(), d.pts + sbase, (size_t)n * 16));
             std::vector<int> v(n);
             for (int i = 0; i < n; ++i) memcpy(&v[i], &p[i].w, 4);
             put_i(v); return SP_OK;
         }
         if (sub == "root") {
-            std::vector<int> r(n), cs(n); CK(d2h(r.data(), d.root + s * N, (size_t)n * 4)); CK(d2h(cs.data(), d.csize + s * N, (size_t)n * 4));
+            std::vector<int> r(n), cs(n); CK(d2h(r.data(), d.root + sbase, (size_t)n * 4)); CK(d2h(cs.data(), d.csize + sbase, (size_t)n * 4));
             for (int i = 0; i < n; ++i) { const int sz = cs[r[i]]; if (sz < ctx->d.c.min_c || sz > ctx->d.c.max_c) r[i] = -1; }
             put_i(r); return SP_OK;
         }
@@ -1017,7 +1020,7 @@ static int tap_build(sp_ctx *ctx, int frame, const std::string &name, std::vecto
             std::vector<SpSegPlane> ch(SP_PSEG); std::vector<int> nx(SP_PSEG); std::vector<SpMergedPlane> mp(SP_PSEG);
             CK(d2h(ch.data(), d.chunks + s * SP_PSEG, sizeof(SpSegPlane) * SP_PSEG)); CK(d2h(nx.data(), d.chunk_next + s * SP_PSEG, 4 * SP_PSEG));
             CK(d2h(mp.data(), d.merged + s * SP_PSEG, sizeof(SpMergedPlane) * SP_PSEG));
-            std::vector<int> pp(n); CK(d2h(pp.data(), d.plane_pts + s * N, (size_t)n * 4));
+            std::vector<int> pp(n); CK(d2h(pp.data(), d.plane_pts + sbase, (size_t)n * 4));
             std::vector<float> coef; std::vector<int> cnt, idx;
             if (seg) {
                 for (int i = 0; i < nseg; ++i) { coef.insert(coef.end(), ch[i].coef, ch[i].coef + 4); cnt.push_back(ch[i].count); idx.insert(idx.end(), pp.begin() + ch[i].off, pp.begin() + ch[i].off + ch[i].count); }

@@ -6,7 +6,7 @@
  *   xyzw, nrm             [B][N] float4    levelled + masked points {x, y, z, 0} and normals {nx, ny, nz, 0} (pixel order)
  *   key/val (x2)          [B*N]  u64/u32   (frame << 32 | voxel index) and pixel index, before/after the radix sort
  *   rep, code             [B][N]           per sorted position: voxel representative pixel and its class bits
- *   "segments"            s = 2*frame + {0: horizontal set, 1: vertical set}; every per-segment array has capacity N
+ *   "segments"            s = 2*frame + {0: horizontal set, 1: vertical set}; the two segments of a frame share a slice of N entries
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -97,7 +97,7 @@ struct SpDev {
     int *voxel_idx;            /* [B][N] */
     unsigned char *voxel_code; /* [B][N] */
     /* segments */
-    float4 *pts;               /* [2B][N] {x, y, z, pixel} */
+    float4 *pts;               /* [B][N] {x, y, z, pixel}: the horizontal set of a frame, then its vertical set (sp_seg_base) */
     int *seg_n;                /* [2B] */
     int *ccnt;                 /* [2B][1 << SP_HASH_BITS] points per cell bucket (zero between chunks) */
     int *cstart;               /* [2B][(1 << SP_HASH_BITS) + 1] exclusive scan of ccnt */
@@ -127,6 +127,11 @@ struct SpDev {
     const int *rnd;            /* SP_RAND_LEN draws of glibc rand() from seed 1 */
     int *flags;                /* [B] capacity flags */
 };
+
+/* A frame's horizontal (s = 2f) and vertical (s = 2f + 1) point sets share ONE slice of N entries of every per-segment array:
+ * both are subsets of the frame's voxel representatives, so together they never exceed N; the vertical set starts where the
+ * horizontal one ends (seg_n is final once k_scan_blocks has run). */
+__device__ __forceinline__ size_t sp_seg_base(const SpDev &d, int s) { return (size_t)(s >> 1) * d.N + ((s & 1) ? (size_t)d.seg_n[s - 1] : 0); }
 
 __device__ __forceinline__ int sp_f2ord(float f) { int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
 __device__ __forceinline__ float sp_ord2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }

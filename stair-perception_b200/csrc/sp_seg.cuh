@@ -30,7 +30,7 @@ __device__ __forceinline__ unsigned sp_point_bucket(const float4 &p, float cell,
 __global__ void __launch_bounds__(256) k_cl_count(SpDev d)
 {
     const int s = blockIdx.y, n = d.seg_n[s];
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
     const float cell = d.c.cell;
     const int lane = threadIdx.x & 31;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(1024) k_cl_scan(SpDev d)
 __global__ void __launch_bounds__(256) k_cl_scatter(SpDev d)
 {
     const int s = blockIdx.y, n = d.seg_n[s];
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     const float cell = d.c.cell;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(1024) k_cl_runs(SpDev d)
     __shared__ int wmax[32];
     __shared__ int carry;
     const int s = blockIdx.x, n = d.seg_n[s];
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     const float4 *pts = d.pts + base;
     int *parent = d.parent + base;
     const float r2 = d.c.r2;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
 {
     __shared__ int2 queue[8][96];
     const int s = blockIdx.y, n = d.seg_n[s];
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     int *parent = d.parent + base;
     const float4 *sp = d.spts + base;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
 __global__ void __launch_bounds__(256) k_cl_flatten(SpDev d)
 {
     const int s = blockIdx.y, n = d.seg_n[s];
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     int *parent = d.parent + base;
     const int lane = threadIdx.x & 31;
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(RK_THREADS) k_cl_rank(SpDev d)
     __shared__ int cnt[RK_WARPS][SP_CMAX + 1];
     __shared__ int nc, nvalid;
     const int s = blockIdx.x, n = d.seg_n[s];
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     int *crank = d.parent + base;                       /* union-find storage is free again: cluster rank per root position */
     if (threadIdx.x == 0) { nc = 0; nvalid = 0; }
     __syncthreads();
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_ransac(SpDev d)
     const int s = blockIdx.y, ci = blockIdx.x;
     if (ci >= d.n_cand[s]) return;
     const bool vertical = (s & 1) != 0;
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int off = d.cand_off[s * SP_CMAX + ci];
     /* current / other point buffers of this cluster (ping-pong across extractions) */
@@ -693,7 +693,7 @@ __device__ __forceinline__ int mg_point(const SpDev &d, int s, const SpSegPlane 
     int c = head;
     while (c >= 0 && k >= chunks[c].count) { k -= chunks[c].count; c = nxt[c]; }
     if (c < 0) return -1;
-    return d.plane_pts[(size_t)s * d.N + chunks[c].off + k];
+    return d.plane_pts[sp_seg_base(d, s) + chunks[c].off + k];
 }
 
 __global__ void __launch_bounds__(MG_WARPS * 32) k_merge(SpDev d, int nB)
@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
     const SpMergedPlane mp = d.merged[s * SP_PSEG + m];
     const SpSegPlane *chunks = d.chunks + s * SP_PSEG;
     const int *nxt = d.chunk_next + s * SP_PSEG;
-    const size_t base = (size_t)s * d.N;
+    const size_t base = sp_seg_base(d, s);
     const float *PX = d.plane_x + base, *PY = d.plane_y + base, *PZ = d.plane_z + base;
     const int *PP = d.plane_pts + base;
     if (tid == 0) {
@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(256) k_gather_plane_points(SpDev d, const int 
     const SpSegPlane *chunks = d.chunks + s * SP_PSEG;
     const int *nxt = d.chunk_next + s * SP_PSEG;
     int *dst = d.plane_idx + (size_t)f * d.N + R.planes[pl].first;
-    const int *PP = d.plane_pts + (size_t)s * d.N;
+    const int *PP = d.plane_pts + sp_seg_base(d, s);
     int c = d.merged[s * SP_PSEG + m].head, w = 0;
     while (c >= 0) {
         const int cnt = chunks[c].count, off = chunks[c].off;

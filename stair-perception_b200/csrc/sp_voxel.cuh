@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
     if (blockIdx.x * 1024 >= M) return;
     const int *blk = d.blk + ((size_t)f * d.nblk + blockIdx.x) * 5;
     int b_head = blk[0], b_h = blk[3], b_v = blk[4];
+    const int nH = d.seg_n[2 * f];                                        /* k_scan_blocks has the frame totals */
     for (int q = 0; q < 4; ++q) {
         const int j = blockIdx.x * 1024 + q * 256 + threadIdx.x;
         const unsigned char code = j < M ? d.code[base + j] : 0;
@@ -388,8 +389,8 @@ __global__ void __launch_bounds__(256) k_scatter_lists(SpDev d)
         const int pk = sp_block_scan_flags3((code & SPC_HEAD) != 0, (code & SPC_H) != 0, (code & SPC_V) != 0, wsum, &tot);
         const int ph = pk & 1023, pH = (pk >> 10) & 1023, pV = pk >> 20;
         if (code & SPC_HEAD) { d.voxel_idx[base + b_head + ph] = rep; d.voxel_code[base + b_head + ph] = code; }
-        if (code & SPC_H) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f) * N + b_h + pH] = pw; }
-        if (code & SPC_V) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[(size_t)(2 * f + 1) * N + b_v + pV] = pw; }
+        if (code & SPC_H) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[base + b_h + pH] = pw; }
+        if (code & SPC_V) { float4 pw = d.xyzw[base + rep]; pw.w = __int_as_float(rep); d.pts[base + nH + b_v + pV] = pw; }   /* the vertical set follows the horizontal one */
         b_head += tot & 1023; b_h += (tot >> 10) & 1023; b_v += tot >> 20;
     }
 }
