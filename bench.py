@@ -423,7 +423,7 @@ def main():
         gather_ms = timed(lambda: shard.gather_compact(cbuf, nb, host_out=h_all), 5) / 5
 
     # the dominant streaming kernel alone (K1K2 = ingest + levelling + masking + organised normals), CUDA events on its stream
-    nb = min(args.max_batch, Fl)
+    nb = min(256, args.max_batch, Fl)                         # 256 frames per launch: what the committed ncu captures ran
     k_ms = []
     for i in range(3 + 10):
         off = (i % max(1, Fl // nb)) * nb
