@@ -184,15 +184,27 @@ __global__ void __launch_bounds__(1024) k_cl_runs(SpDev d)
  * component's root is its smallest member position whatever the visiting order.
  * The distance tests run warp-converged; the edges they find are pushed to a per-warp queue and united 32 at a
  * time, so the (divergent, pointer-chasing) union-find code always runs with a full warp. */
-__global__ void __launch_bounds__(256) k_cl_union(SpDev d)
+/* hash contribution of the k-th cell offset (own cell, then the 13 forward ones): (a + da) * P = a * P + da * P */
+__constant__ unsigned c_cl_dhash[14][3] = {
+#define SP_CL_DH(k) { (unsigned)((k) / 9 - 1) * 73856093u, (unsigned)(((k) / 3) % 3 - 1) * 19349663u, (unsigned)((k) % 3 - 1) * 83492791u }
+    SP_CL_DH(13), SP_CL_DH(14), SP_CL_DH(15), SP_CL_DH(16), SP_CL_DH(17), SP_CL_DH(18), SP_CL_DH(19), SP_CL_DH(20), SP_CL_DH(21), SP_CL_DH(22),
+    SP_CL_DH(23), SP_CL_DH(24), SP_CL_DH(25), SP_CL_DH(26)
+#undef SP_CL_DH
+};
+
+#define CU_W 2                                                           /* candidates per lane and iteration */
+__global__ void __launch_bounds__(256, 8) k_cl_union(SpDev d)
 {
-    __shared__ int2 queue[8][96];
+    __shared__ int2 queue[8][32 + 32 * CU_W];
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = sp_seg_base(d, s);
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     int *parent = d.parent + base;
     const float4 *sp = d.spts + base;
-    const float cell = d.c.cell, r2 = d.c.r2;
+    float r2 = d.c.r2;
+    asm volatile("" : "+l"(parent), "+l"(sp), "+f"(r2));                 /* keep the segment's bases and r2 in registers: one IMAD.WIDE per address */
+    __builtin_assume(__isGlobal(parent)); __builtin_assume(__isGlobal(sp));
+    const float cell = d.c.cell;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     int2 *q = queue[wid];
@@ -201,48 +213,57 @@ __global__ void __launch_bounds__(256) k_cl_union(SpDev d)
         const int t = t0 + lane;
         const bool act = t < n;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        int oi = 0, a = 0, b = 0, c = 0; unsigned h0 = 0;
-        if (act) { p = sp[t]; oi = __float_as_int(p.w); h0 = sp_point_bucket(p, cell, a, b, c); }
-        for (int k = 13; k < 27; ++k) {                                  /* offsets (0,0,0) then the 13 forward ones */
+        int oi = 0; unsigned ha = 0u, hb = 0u, hc = 0u;
+        if (act) {
+            p = sp[t]; oi = __float_as_int(p.w);
+            ha = (unsigned)(int)floorf(p.x / cell) * 73856093u; hb = (unsigned)(int)floorf(p.y / cell) * 19349663u; hc = (unsigned)(int)floorf(p.z / cell) * 83492791u;
+        }
+        /* "same parent already" filter: a parent of oi read earlier is still a member of oi's tree, so equality with a
+         * candidate's parent proves the two connected; re-read after this warp's own unions */
+        int poi = act ? parent[oi] : 0;
+        for (int k = 0; k < 14; ++k) {                                   /* offsets (0,0,0) then the 13 forward ones */
             int j = 0, j1 = 0;
             if (act) {
-                const int da = k / 9 - 1, db = (k / 3) % 3 - 1, dc = k % 3 - 1;
-                const unsigned h = k == 13 ? h0 : (sp_cell_hash(a + da, b + db, c + dc) & ((1u << SP_HASH_BITS) - 1u));
+                const unsigned h = ((ha + c_cl_dhash[k][0]) ^ (hb + c_cl_dhash[k][1]) ^ (hc + c_cl_dhash[k][2])) & ((1u << SP_HASH_BITS) - 1u);
                 j = start[h]; j1 = start[h + 1];
             }
-            const int own_limit = k == 13 ? oi : 0x7fffffff;             /* own cell: only members with a smaller list position */
+            const int own_limit = k == 0 ? oi : 0x7fffffff;              /* own cell: only members with a smaller list position */
             const int trips = __reduce_max_sync(0xffffffffu, j1 - j);     /* warp-uniform trip count */
-            for (int it = 0; it < trips; it += 2) {
-                bool hit0 = false, hit1 = false; int oj0 = 0, oj1 = 0;
-                if (j < j1) {
-                    const float4 qq = sp[j];
-                    oj0 = __float_as_int(qq.w);
-                    const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
-                    float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
-                    hit0 = dist < r2 && oj0 < own_limit;
+            const float4 *pj = sp + j;
+            for (int it = 0; it < trips; it += CU_W, j += CU_W, pj += CU_W) {
+                int oj[CU_W], par[CU_W];
+                bool hit[CU_W];
+#pragma unroll
+                for (int u = 0; u < CU_W; ++u) {
+                    hit[u] = false; oj[u] = 0;
+                    if (j + u < j1) {
+                        const float4 qq = pj[u];
+                        oj[u] = __float_as_int(qq.w);
+                        const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
+                        float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
+                        hit[u] = dist < r2 && oj[u] < own_limit;
+                    }
                 }
-                if (j + 1 < j1) {
-                    const float4 qq = sp[j + 1];
-                    oj1 = __float_as_int(qq.w);
-                    const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
-                    float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;
-                    hit1 = dist < r2 && oj1 < own_limit;
-                }
-                j += 2;
-                if (hit0) hit0 = parent[oi] != parent[oj0];
-                if (hit1) hit1 = parent[oi] != parent[oj1];
-                const unsigned b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
-                if (b0 | b1) {
-                    if (hit0) q[qn + __popc(b0 & lt)] = make_int2(oi, oj0);
-                    qn += __popc(b0);
-                    if (hit1) q[qn + __popc(b1 & lt)] = make_int2(oi, oj1);
-                    qn += __popc(b1);
+#pragma unroll
+                for (int u = 0; u < CU_W; ++u) { par[u] = poi; if (hit[u]) par[u] = parent[(unsigned)oj[u]]; }
+                unsigned bal[CU_W], any = 0u;
+#pragma unroll
+                for (int u = 0; u < CU_W; ++u) { bal[u] = __ballot_sync(0xffffffffu, par[u] != poi); any |= bal[u]; }
+                if (any) {
+#pragma unroll
+                    for (int u = 0; u < CU_W; ++u) {
+                        if (par[u] != poi) q[qn + __popc(bal[u] & lt)] = make_int2(oi, oj[u]);
+                        qn += __popc(bal[u]);
+                    }
                     __syncwarp();
-                    while (qn >= 32) {
-                        const int2 e = q[qn - 32 + lane];
-                        qn -= 32;
-                        __syncwarp();
-                        sp_uf_unite(parent, e.x, e.y);
+                    if (qn >= 32) {
+                        do {
+                            const int2 e = q[qn - 32 + lane];
+                            qn -= 32;
+                            __syncwarp();
+                            sp_uf_unite(parent, e.x, e.y);
+                        } while (qn >= 32);
+                        if (act) poi = parent[oi];
                     }
                 }
             }
