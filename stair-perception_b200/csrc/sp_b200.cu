@@ -78,6 +78,7 @@ void make_consts(const sp_params &p, SpConst &c)
     const double radius = (double)(float)p.cluster_tolerance;
     c.r2 = (float)(radius * radius);
     c.cell = (float)radius * 1.0001f;
+    c.inv_cell = 1.0f / c.cell;
     c.min_c = p.min_cluster_size; c.max_c = p.max_cluster_size;
     c.seg_thr = (float)p.seg_threshold;
     c.sin_angle = fabs(sin((double)deg2radf((float)p.seg_plane_angle_diff)));

@@ -61,7 +61,7 @@ struct SpConst {               /* derived parameters, narrowed exactly where the
     float ivx, ivy, ivz;                 /* 1.0f / leaf (voxel_grid_indices.h:131) */
     float noleg_th2;                     /* th*th, th = (float)noleg_distance */
     float h_ge, h_le, v_lo, v_hi;        /* a8 as float cut-points on nx (see sp_b200.cu: make_cutpoints) */
-    float r2, cell;                      /* clustering */
+    float r2, cell, inv_cell;            /* clustering: cell edge = tolerance x 1.0001, points are binned by x * (1 / edge) */
     int min_c, max_c;
     float seg_thr;
     double sin_angle;

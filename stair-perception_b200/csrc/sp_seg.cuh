@@ -21,9 +21,11 @@ __device__ __forceinline__ unsigned sp_cell_hash(int a, int b, int c)
 /* Cell grid of one segment: cell edge = cluster tolerance (x 1.0001), cells hashed into 1 << SP_HASH_BITS buckets.
  * Three passes lay the points out bucket-major (a counting sort): count, scan, scatter.  Points of different
  * cells that share a bucket are told apart by the distance test itself. */
-__device__ __forceinline__ unsigned sp_point_bucket(const float4 &p, float cell, int &a, int &b, int &c)
+__device__ __forceinline__ unsigned sp_point_bucket(const float4 &p, float inv_cell, int &a, int &b, int &c)
 {
-    a = (int)floorf(p.x / cell); b = (int)floorf(p.y / cell); c = (int)floorf(p.z / cell);
+    /* any consistent binning with cells no narrower than the tolerance is valid: the 1e-4 margin of the edge covers the rounding
+     * of the product for |coordinate| < 800 cells */
+    a = (int)floorf(p.x * inv_cell); b = (int)floorf(p.y * inv_cell); c = (int)floorf(p.z * inv_cell);
     return sp_cell_hash(a, b, c) & ((1u << SP_HASH_BITS) - 1u);
 }
 
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(256) k_cl_count(SpDev d)
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = sp_seg_base(d, s);
     int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
-    const float cell = d.c.cell;
+    const float cell = d.c.inv_cell;
     const int lane = threadIdx.x & 31;
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + lane;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) k_cl_scatter(SpDev d)
     const size_t base = sp_seg_base(d, s);
     int *cnt = d.ccnt + ((size_t)s << SP_HASH_BITS);
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
-    const float cell = d.c.cell;
+    const float cell = d.c.inv_cell;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
@@ -178,94 +180,115 @@ __global__ void __launch_bounds__(1024) k_cl_runs(SpDev d)
     }
 }
 
-/* One thread per point in bucket-major order.  Every unordered pair of points in adjacent cells is tested exactly
- * once: own cell against members with a smaller list position, plus the 13 "forward" neighbour cells.  (Two cells
- * sharing a bucket only cause repeated, idempotent unions.)  Union-find is indexed by list position, so a
- * component's root is its smallest member position whatever the visiting order.
- * The distance tests run warp-converged; the edges they find are pushed to a per-warp queue and united 32 at a
- * time, so the (divergent, pointer-chasing) union-find code always runs with a full warp. */
-/* hash contribution of the k-th cell offset (own cell, then the 13 forward ones): (a + da) * P = a * P + da * P */
-__constant__ unsigned c_cl_dhash[14][3] = {
-#define SP_CL_DH(k) { (unsigned)((k) / 9 - 1) * 73856093u, (unsigned)(((k) / 3) % 3 - 1) * 19349663u, (unsigned)((k) % 3 - 1) * 83492791u }
-    SP_CL_DH(13), SP_CL_DH(14), SP_CL_DH(15), SP_CL_DH(16), SP_CL_DH(17), SP_CL_DH(18), SP_CL_DH(19), SP_CL_DH(20), SP_CL_DH(21), SP_CL_DH(22),
-    SP_CL_DH(23), SP_CL_DH(24), SP_CL_DH(25), SP_CL_DH(26)
-#undef SP_CL_DH
-};
-
-#define CU_W 2                                                           /* candidates per lane and iteration */
+/* One warp per cell.  A warp takes a window of 32 positions of the bucket-major point array and handles the buckets that START in
+ * it.  For a cell (the points of a bucket with equal cell coordinates; a bucket shared by two cells is split) lanes 0..13 look up
+ * the own bucket and the 13 "forward" neighbour buckets, and the concatenation of those ranges is the CANDIDATE list: 32 candidates
+ * at a time sit one per lane -- loaded once per cell, not once per member point -- and the cell's points are broadcast from shared
+ * memory one after the other, so every distance test runs with a full warp and every unordered pair of points in adjacent cells is
+ * tested once (twice inside the own cell).
+ * Edges: lanes keep the set of candidate lanes known to be connected already (start: equal parent, i.e. same tree); a member that
+ * reaches several of those sets emits ONE edge per set (none to the set that holds the member itself) and merges them, so a cell
+ * hands a spanning forest of its little graph to the union-find instead of every close pair.  Edges go to a per-warp queue and are
+ * united 32 at a time (lock-free union-find on list positions, smaller index wins: a component's root is its smallest member
+ * whatever the visiting order). */
 __global__ void __launch_bounds__(256, 8) k_cl_union(SpDev d)
 {
-    __shared__ int2 queue[8][32 + 32 * CU_W];
+    __shared__ int2 queue[8][64];
+    __shared__ float4 memb[8][32];
+    __shared__ int rstart[8][16], roff[8][16];
     const int s = blockIdx.y, n = d.seg_n[s];
     const size_t base = sp_seg_base(d, s);
     const int *start = d.cstart + (size_t)s * ((1 << SP_HASH_BITS) + 1);
     int *parent = d.parent + base;
     const float4 *sp = d.spts + base;
     float r2 = d.c.r2;
-    asm volatile("" : "+l"(parent), "+l"(sp), "+f"(r2));                 /* keep the segment's bases and r2 in registers: one IMAD.WIDE per address */
-    __builtin_assume(__isGlobal(parent)); __builtin_assume(__isGlobal(sp));
-    const float cell = d.c.cell;
+    asm volatile("" : "+l"(parent), "+l"(sp), "+l"(start), "+f"(r2));    /* keep the segment's bases and r2 in registers: one IMAD.WIDE per address */
+    __builtin_assume(__isGlobal(parent)); __builtin_assume(__isGlobal(sp)); __builtin_assume(__isGlobal(start));
+    const float cell = d.c.inv_cell;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     int2 *q = queue[wid];
+    float4 *mb = memb[wid];
+    int *rs_ = rstart[wid], *ro_ = roff[wid];
+    const int kk = (lane < 14 ? lane : 0) + 13;                          /* lanes 0..13: cell offset (0,0,0), then the 13 forward ones */
+    const int da = kk / 9 - 1, db = (kk / 3) % 3 - 1, dc = kk % 3 - 1;
     int qn = 0;                                                          /* warp-uniform */
-    for (int t0 = blockIdx.x * blockDim.x + wid * 32; t0 < n; t0 += gridDim.x * blockDim.x) {
+    for (int t0 = (blockIdx.x * 8 + wid) * 32; t0 < n; t0 += gridDim.x * 256) {
         const int t = t0 + lane;
-        const bool act = t < n;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        int oi = 0; unsigned ha = 0u, hb = 0u, hc = 0u;
-        if (act) {
-            p = sp[t]; oi = __float_as_int(p.w);
-            ha = (unsigned)(int)floorf(p.x / cell) * 73856093u; hb = (unsigned)(int)floorf(p.y / cell) * 19349663u; hc = (unsigned)(int)floorf(p.z / cell) * 83492791u;
+        bool first = false; unsigned h = 0u; int hnext = 0;
+        if (t < n) {
+            const float4 p = sp[t];
+            int a, b, c;
+            h = sp_point_bucket(p, cell, a, b, c);
+            first = start[h] == t; hnext = start[h + 1];
         }
-        /* "same parent already" filter: a parent of oi read earlier is still a member of oi's tree, so equality with a
-         * candidate's parent proves the two connected; re-read after this warp's own unions */
-        int poi = act ? parent[oi] : 0;
-        for (int k = 0; k < 14; ++k) {                                   /* offsets (0,0,0) then the 13 forward ones */
-            int j = 0, j1 = 0;
-            if (act) {
-                const unsigned h = ((ha + c_cl_dhash[k][0]) ^ (hb + c_cl_dhash[k][1]) ^ (hc + c_cl_dhash[k][2])) & ((1u << SP_HASH_BITS) - 1u);
-                j = start[h]; j1 = start[h + 1];
-            }
-            const int own_limit = k == 0 ? oi : 0x7fffffff;              /* own cell: only members with a smaller list position */
-            const int trips = __reduce_max_sync(0xffffffffu, j1 - j);     /* warp-uniform trip count */
-            const float4 *pj = sp + j;
-            for (int it = 0; it < trips; it += CU_W, j += CU_W, pj += CU_W) {
-                int oj[CU_W], par[CU_W];
-                bool hit[CU_W];
-#pragma unroll
-                for (int u = 0; u < CU_W; ++u) {
-                    hit[u] = false; oj[u] = 0;
-                    if (j + u < j1) {
-                        const float4 qq = pj[u];
-                        oj[u] = __float_as_int(qq.w);
-                        const float d0 = p.x - qq.x, d1 = p.y - qq.y, d2 = p.z - qq.z;
-                        float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order */
-                        hit[u] = dist < r2 && oj[u] < own_limit;
+        unsigned firsts = __ballot_sync(0xffffffffu, first);
+        while (firsts) {                                                 /* buckets that start in this window */
+            const int fl = __ffs(firsts) - 1;
+            firsts &= firsts - 1;
+            const int j0 = t0 + fl, j1 = __shfl_sync(0xffffffffu, hnext, fl);
+            for (int m0 = j0; m0 < j1; m0 += 32) {                       /* the bucket's points, 32 at a time */
+                const int mi = m0 + lane;
+                const bool ism = mi < j1;
+                int am = 0, bm = 0, cm = 0;
+                if (ism) { const float4 pm = sp[mi]; sp_point_bucket(pm, cell, am, bm, cm); mb[lane] = pm; }
+                unsigned todo = __ballot_sync(0xffffffffu, ism);
+                while (todo) {                                           /* cells of the bucket (one, unless two cells share it) */
+                    const int gl = __ffs(todo) - 1;
+                    const int ga = __shfl_sync(0xffffffffu, am, gl), gb = __shfl_sync(0xffffffffu, bm, gl), gc = __shfl_sync(0xffffffffu, cm, gl);
+                    unsigned gm = __ballot_sync(0xffffffffu, ism && am == ga && bm == gb && cm == gc);
+                    todo &= ~gm;
+                    int rs = 0, rc = 0;
+                    if (lane < 14) {
+                        const unsigned hk = sp_cell_hash(ga + da, gb + db, gc + dc) & ((1u << SP_HASH_BITS) - 1u);
+                        rs = start[hk]; rc = start[hk + 1] - rs;
                     }
-                }
+                    int inc = rc;
 #pragma unroll
-                for (int u = 0; u < CU_W; ++u) { par[u] = poi; if (hit[u]) par[u] = parent[(unsigned)oj[u]]; }
-                unsigned bal[CU_W], any = 0u;
-#pragma unroll
-                for (int u = 0; u < CU_W; ++u) { bal[u] = __ballot_sync(0xffffffffu, par[u] != poi); any |= bal[u]; }
-                if (any) {
-#pragma unroll
-                    for (int u = 0; u < CU_W; ++u) {
-                        if (par[u] != poi) q[qn + __popc(bal[u] & lt)] = make_int2(oi, oj[u]);
-                        qn += __popc(bal[u]);
-                    }
+                    for (int o = 1; o < 16; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                    if (lane < 16) { rs_[lane] = rs; ro_[lane] = inc - rc; }
+                    const int C = __shfl_sync(0xffffffffu, inc, 15);
                     __syncwarp();
-                    if (qn >= 32) {
-                        do {
-                            const int2 e = q[qn - 32 + lane];
-                            qn -= 32;
-                            __syncwarp();
-                            sp_uf_unite(parent, e.x, e.y);
-                        } while (qn >= 32);
-                        if (act) poi = parent[oi];
+                    for (int c0 = 0; c0 < C; c0 += 32) {                 /* candidates, 32 at a time */
+                        const int ci = c0 + lane;
+                        const bool isc = ci < C;
+                        int k = 0;                                       /* the range ci falls in: largest k with ro_[k] <= ci */
+                        if (ro_[k + 8] <= ci) k += 8;
+                        if (ro_[k + 4] <= ci) k += 4;
+                        if (ro_[k + 2] <= ci) k += 2;
+                        if (ro_[k + 1] <= ci) k += 1;
+                        float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int oj = -1, pc = -1 - lane;
+                        if (isc) { qq = sp[(unsigned)(rs_[k] + (ci - ro_[k]))]; oj = __float_as_int(qq.w); pc = parent[(unsigned)oj]; }
+                        unsigned comp = __match_any_sync(0xffffffffu, pc);       /* candidates of one tree */
+                        for (unsigned g = gm; g; g &= g - 1) {
+                            const float4 pm = mb[__ffs(g) - 1];
+                            const float d0 = pm.x - qq.x, d1 = pm.y - qq.y, d2 = pm.z - qq.z;
+                            float dist = d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order (0 + d0 * d0 == d0 * d0) */
+                            const bool hit = isc && dist < r2;
+                            const int oi = __float_as_int(pm.w);
+                            const unsigned self = __ballot_sync(0xffffffffu, hit && oj == oi);
+                            if (__any_sync(0xffffffffu, hit && (comp & self) == 0u)) {          /* reaches a set it is not known to be in */
+                                const unsigned H = __ballot_sync(0xffffffffu, hit);
+                                const unsigned U = __reduce_or_sync(0xffffffffu, hit ? comp : 0u);
+                                const bool lead = hit && lane == __ffs(comp & H) - 1 && (comp & self) == 0u;
+                                const unsigned L = __ballot_sync(0xffffffffu, lead);
+                                if (lead) q[qn + __popc(L & lt)] = make_int2(oi, oj);
+                                qn += __popc(L);
+                                if ((U >> lane) & 1u) comp = U | self;
+                                __syncwarp();
+                                while (qn >= 32) {
+                                    const int2 e = q[qn - 32 + lane];
+                                    qn -= 32;
+                                    __syncwarp();
+                                    sp_uf_unite(parent, e.x, e.y);
+                                }
+                            }
+                        }
                     }
+                    __syncwarp();                                        /* ro_ / rs_ are rewritten by the next cell */
                 }
+                __syncwarp();                                            /* mb is rewritten by the next chunk */
             }
         }
     }
