@@ -257,25 +257,28 @@ __global__ void __launch_bounds__(256, 8) k_cl_union(SpDev d)
                         if (ro_[k + 4] <= ci) k += 4;
                         if (ro_[k + 2] <= ci) k += 2;
                         if (ro_[k + 1] <= ci) k += 1;
-                        float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 qq = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);        /* no candidate: NaN fails every test */
                         int oj = -1, pc = -1 - lane;
                         if (isc) { qq = sp[(unsigned)(rs_[k] + (ci - ro_[k]))]; oj = __float_as_int(qq.w); pc = parent[(unsigned)oj]; }
                         unsigned comp = __match_any_sync(0xffffffffu, pc);       /* candidates of one tree */
+                        /* range 0 is the own bucket, in member order: member lane ml of this chunk is candidate m0 - j0 + ml */
+                        const int self0 = m0 - j0 - c0;
                         for (unsigned g = gm; g; g &= g - 1) {
-                            const float4 pm = mb[__ffs(g) - 1];
+                            const int ml = __ffs(g) - 1;
+                            const float4 pm = mb[ml];
                             const float d0 = pm.x - qq.x, d1 = pm.y - qq.y, d2 = pm.z - qq.z;
                             float dist = d0 * d0; dist += d1 * d1; dist += d2 * d2;   /* flann::L2_Simple order (0 + d0 * d0 == d0 * d0) */
-                            const bool hit = isc && dist < r2;
-                            const int oi = __float_as_int(pm.w);
-                            const unsigned self = __ballot_sync(0xffffffffu, hit && oj == oi);
+                            const bool hit = dist < r2;
+                            const unsigned self = (unsigned)(self0 + ml) < 32u ? 1u << (self0 + ml) : 0u;
                             if (__any_sync(0xffffffffu, hit && (comp & self) == 0u)) {          /* reaches a set it is not known to be in */
+                                const int oi = __float_as_int(pm.w);
                                 const unsigned H = __ballot_sync(0xffffffffu, hit);
                                 const unsigned U = __reduce_or_sync(0xffffffffu, hit ? comp : 0u);
                                 const bool lead = hit && lane == __ffs(comp & H) - 1 && (comp & self) == 0u;
                                 const unsigned L = __ballot_sync(0xffffffffu, lead);
                                 if (lead) q[qn + __popc(L & lt)] = make_int2(oi, oj);
                                 qn += __popc(L);
-                                if ((U >> lane) & 1u) comp = U | self;
+                                if ((U >> lane) & 1u) comp = U;
                                 __syncwarp();
                                 while (qn >= 32) {
                                     const int2 e = q[qn - 32 + lane];
