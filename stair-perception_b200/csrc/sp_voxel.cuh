@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(VX_T) k_vx_scan(SpDev d, int p)
 /* one tile: stable rank of every key among the tile's keys of the same digit, then the scatter */
 __global__ void __launch_bounds__(VX_T, 3) k_vx_scatter(SpDev d, int p)
 {
-    __shared__ unsigned wc[VX_NW][VX_BINS];
+    __shared__ __align__(16) unsigned wc[VX_NW][VX_BINS];                    /* per-warp digit counters, then the staged pairs */
+    __shared__ unsigned off[VX_BINS], wsum[VX_NW];
     const int f = blockIdx.y, tile = blockIdx.x;
     const SpFrameGrid g = d.grid[f];
     if (p >= g.npass || tile * VX_TILE >= g.M) return;
@@ -192,37 +193,65 @@ __global__ void __launch_bounds__(VX_T, 3) k_vx_scatter(SpDev d, int p)
     const unsigned *sk = reinterpret_cast<const unsigned *>((p & 1) ? d.key_b : d.key_a) + sl, *sv = ((p & 1) ? d.val_b : d.val_a) + sl;
     unsigned *dk = reinterpret_cast<unsigned *>((p & 1) ? d.key_a : d.key_b) + sl, *dv = ((p & 1) ? d.val_a : d.val_b) + sl;
     const int shift = p * VX_RB;
-    for (int k = lane; k < VX_BINS; k += 32) wc[wid][k] = 0u;
+    for (int k = lane; k < VX_BINS / 4; k += 32) reinterpret_cast<uint4 *>(wc[wid])[k] = make_uint4(0u, 0u, 0u, 0u);
     const int cb = tile * VX_TILE + wid * (32 * VX_E);                       /* warp-striped: position order = (warp, k, lane) */
-    unsigned key[VX_E], val[VX_E], rank[VX_E];
+    unsigned key[VX_E], val[VX_E], rank[VX_E], grp[VX_E];
 #pragma unroll
     for (int k = 0; k < VX_E; ++k) { const int j = cb + k * 32 + lane; key[k] = j < M ? sk[j] : 0u; val[k] = j < M ? sv[j] : 0u; }
+#pragma unroll
+    for (int k = 0; k < VX_E; ++k) {
+        const int j = cb + k * 32 + lane;
+        grp[k] = __match_any_sync(0xffffffffu, j < M ? (key[k] >> shift) & (VX_BINS - 1) : (unsigned)VX_BINS + lane);
+    }
     __syncwarp();
+    /* the first lane of every digit group takes the group's slots from the warp's counter: one shared-memory atomic per group,
+     * the eight rows back to back (a warp's atomics on its own counters complete in program order), instead of eight dependent
+     * read - modify - write round trips */
 #pragma unroll
     for (int k = 0; k < VX_E; ++k) {
         const int j = cb + k * 32 + lane;
-        const unsigned dg = (key[k] >> shift) & (VX_BINS - 1);
-        const unsigned m = __match_any_sync(0xffffffffu, j < M ? dg : (unsigned)VX_BINS + lane);
-        unsigned prev = 0;
-        if (j < M) prev = wc[wid][dg];
+        rank[k] = 0u;
+        if (j < M && (grp[k] & lt) == 0u) rank[k] = atomicAdd(&wc[wid][(key[k] >> shift) & (VX_BINS - 1)], (unsigned)__popc(grp[k]));
         __syncwarp();
-        if (j < M && (m & lt) == 0) wc[wid][dg] = prev + __popc(m);
-        __syncwarp();
-        rank[k] = prev + __popc(m & lt);
     }
-    __syncthreads();
-    {                                                                        /* digit tid: where each warp's keys of this tile go */
-        unsigned run = d.vth[((size_t)f * d.ntile + tile) * VX_BINS + tid];
 #pragma unroll
-        for (int w = 0; w < VX_NW; ++w) { const unsigned c = wc[w][tid]; wc[w][tid] = run; run += c; }
+    for (int k = 0; k < VX_E; ++k) rank[k] = __shfl_sync(0xffffffffu, rank[k], __ffs(grp[k]) - 1) + __popc(grp[k] & lt);
+    __syncthreads();
+    {   /* digit tid: the tile's keys of this digit, warp by warp -> position of each (warp, digit) group in the tile sorted by digit */
+        unsigned tot = 0u;
+#pragma unroll
+        for (int w = 0; w < VX_NW; ++w) { const unsigned c = wc[w][tid]; wc[w][tid] = tot; tot += c; }
+        unsigned inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        unsigned before = 0u;
+        for (int w = 0; w < wid; ++w) before += wsum[w];
+        const unsigned ls = before + inc - tot;                              /* tile-local start of the digit */
+        off[tid] = d.vth[((size_t)f * d.ntile + tile) * VX_BINS + tid] - ls; /* local position -> destination */
+#pragma unroll
+        for (int w = 0; w < VX_NW; ++w) wc[w][tid] += ls;
     }
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VX_E; ++k) rank[k] += wc[wid][(key[k] >> shift) & (VX_BINS - 1)];      /* tile-local sorted position */
+    __syncthreads();
+    /* the pairs go through shared memory (over the counters) in digit order, so that neighbouring threads write neighbouring
+     * destinations: a digit's keys of a tile are a run of ~8 consecutive words = whole 32-byte sectors, where the direct scatter
+     * sent 32 partial sectors per store instruction to L2 */
+    uint2 *stage = reinterpret_cast<uint2 *>(&wc[0][0]);
+#pragma unroll
+    for (int k = 0; k < VX_E; ++k) { const int j = cb + k * 32 + lane; if (j < M) stage[rank[k]] = make_uint2(key[k], val[k]); }
+    __syncthreads();
+    const int cnt = min(VX_TILE, M - tile * VX_TILE);
 #pragma unroll
     for (int k = 0; k < VX_E; ++k) {
-        const int j = cb + k * 32 + lane;
-        if (j < M) {
-            const unsigned pos = wc[wid][(key[k] >> shift) & (VX_BINS - 1)] + rank[k];
-            dk[pos] = key[k]; dv[pos] = val[k];
+        const int i = k * VX_T + tid;
+        if (i < cnt) {
+            const uint2 e = stage[i];
+            const unsigned pos = off[(e.x >> shift) & (VX_BINS - 1)] + (unsigned)i;
+            dk[pos] = e.x; dv[pos] = e.y;
         }
     }
 }
