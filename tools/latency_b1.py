@@ -30,3 +30,29 @@ for graph in ("0", "8"):
         assert out.tobytes() == ref.tobytes()
         print("SP_GRAPH=%s %-14s median %.3f ms  min %.3f ms  planes %d" % (graph, name, float(np.median(ts)), min(ts), int(out[0]["n_planes"])))
     ctx.close()
+
+# where the millisecond goes: the same frame from pinned host memory and from device memory
+import torch  # noqa: E402
+
+os.environ["SP_GRAPH"] = "8"
+ctx = sp.Context(device=0, width=512, height=424, max_batch=1)
+ctx.set_trace(True)
+pin = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).pin_memory()
+dev = pin.cuda()
+Rd = torch.from_numpy(R.reshape(1, 9).copy()).cuda()
+torch.cuda.synchronize()
+for name, fn in (("pageable host", lambda: ctx.process_frames(rec, R.reshape(1, 9))),
+                 ("pinned host", lambda: ctx.process_frames(pin.numpy().view(rec.dtype), R.reshape(1, 9))),
+                 ("device", lambda: ctx.process_frames(dev, Rd, device_input=True, nframes=1))):
+    for _ in range(5):
+        fn()
+    ts = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        fn()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print("input in %-14s median %.3f ms  min %.3f ms" % (name, float(np.median(ts)), min(ts)))
+print("stage ms:", ctx.stage_ms())
+tr = ctx.trace_ms()
+print("kernel sum %.3f ms: " % sum(ms for _, ms in tr) + ", ".join("%s %.0f us" % (n, 1e3 * ms) for n, ms in tr if ms > 0.008))
+ctx.close()
