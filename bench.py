@@ -453,10 +453,10 @@ def main():
     n_crop = int(res_nb["n_crop"].sum())
     n_vox = int(res_nb["n_voxel"].sum())
     roof_voxel = None
-    vk_ms = tdict.get("k_voxel_key", 0.0)
+    vk_ms = tdict.get("k_vx_key", 0.0)
     if vk_ms > 0:
         vk_bytes = 16 * N * nb + 8 * n_crop
-        roof_voxel = {"bound": "hbm", "kernel": "k_voxel_key", "achieved": vk_bytes / (vk_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        roof_voxel = {"bound": "hbm", "kernel": "k_vx_key", "achieved": vk_bytes / (vk_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                       "frac": vk_bytes / (vk_ms * 1e-3) / 1e9 / peak, "ms_per_launch": vk_ms, "algorithmic_bytes_per_launch": vk_bytes,
                       "note": "timed inside a traced chunk (one CUDA event before and after the launch on the library's stream)"}
     # the whole voxel stage against its compulsory bytes (12 B per point read + 4 B per voxel written)
