@@ -418,9 +418,11 @@ def main():
     assert np.array_equal(results[:N_DISTINCT].view(np.uint8), results[N_DISTINCT:2 * N_DISTINCT].view(np.uint8)) or F < 2 * N_DISTINCT
     # the exchange alone (sizes + compact records + copy to the host), device-timed
     gather_ms = None
+    gather_parts = {}
     if world > 1:
         _, nb = ctx.process_frames_compact(d_clouds, d_R, device_input=True, nframes=Fl, out=cbuf)
         gather_ms = timed(lambda: shard.gather_compact(cbuf, nb, host_out=h_all), 5) / 5
+        shard.gather_compact(cbuf, nb, host_out=h_all, parts=gather_parts)
 
     # the dominant streaming kernel alone (K1K2 = ingest + levelling + masking + organised normals), CUDA events on its stream
     nb = min(256, args.max_batch, Fl)                         # 256 frames per launch: what the committed ncu captures ran
@@ -593,8 +595,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 16 + 36)),
                     "d2h_bytes_per_step": d2h_e, "frames_per_step": Fe, "ms_per_step": ms_e / args.steps,
                     "api": "sp_process_frames_compact from pinned host clouds (H2D inside), exchange, compact records to the host (D2H inside)"},
-            "gather": {"ms": gather_ms, "bytes_per_rank": [int(v) for v in last["sizes"]],
-                       "note": "sizes all-gather + padded all-gather of the compact records (NCCL, device buffers) + concatenation + D2H, device-timed"},
+            "gather": {"ms": gather_ms, "parts_ms_rank0": {k: round(v, 4) for k, v in gather_parts.items()}, "bytes_per_rank": [int(v) for v in last["sizes"]],
+                       "note": "sizes all-gather + padded all-gather of the compact records (NCCL, device buffers) + D2H of the whole gathered batch on EVERY rank (N copies of the same bytes share the host's PCIe / memory path), device-timed"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_ingest_normals", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

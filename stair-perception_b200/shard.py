@@ -56,7 +56,7 @@ def gather_results(local, nframes, group=None, device=None):
 _slots = {}                                                      # the receive buffer of the last gather, reused while the size stays
 
 
-def gather_compact(local, nbytes, group=None, host_out=None):
+def gather_compact(local, nbytes, group=None, host_out=None, parts=None):
     """All-gather of COMPACT records (sp_process_frames_compact: 64-byte header + n_planes plane records per frame) straight
     from device memory: no host bounce, about 3 KB per frame on the wire instead of the 14 400-byte fixed record.
 
@@ -64,7 +64,9 @@ def gather_compact(local, nbytes, group=None, host_out=None):
                capacity must cover the largest rank's byte count (sp_compact_bytes_max(frames of the largest shard) does)
     returns  : (numpy uint8 array with the compact records of the WHOLE batch in batch order, [bytes per rank]); identical on
                every rank.  Shards are contiguous blocks in rank order, so concatenating the ranks' buffers is batch order.
-    host_out : optional pinned torch uint8 CPU tensor to receive the result (avoids a pageable copy)."""
+    host_out : optional pinned torch uint8 CPU tensor to receive the result (avoids a pageable copy).
+    parts    : optional dict; with CUDA tensors it receives the device-timed milliseconds of the three steps
+               (sizes exchange, all-gather of the records, copy of the gathered batch to this rank's host)."""
     import torch
     import torch.distributed as dist
 
@@ -75,9 +77,14 @@ def gather_compact(local, nbytes, group=None, host_out=None):
             return host_out[:nbytes].numpy(), [int(nbytes)]
         return local[:nbytes].cpu().numpy(), [int(nbytes)]
     world = dist.get_world_size(group)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if parts is not None and local.is_cuda else None
+    if ev:
+        ev[0].record()
     sizes_t = torch.empty(world, dtype=torch.int64, device=local.device)
     dist.all_gather_into_tensor(sizes_t, torch.tensor([int(nbytes)], dtype=torch.int64, device=local.device), group=group)
     sizes = [int(v) for v in sizes_t.tolist()]
+    if ev:
+        ev[1].record()
     pad = (max(sizes) + 15) // 16 * 16                          # equal-sized slots: one fixed-size collective
     if local.numel() < pad:
         raise ValueError("compact buffer of %d bytes cannot hold the largest shard (%d bytes)" % (local.numel(), pad))
@@ -92,8 +99,14 @@ def gather_compact(local, nbytes, group=None, host_out=None):
     else:
         packed = torch.cat([slots[r * pad: r * pad + sizes[r]] for r in range(world)])
     total = int(packed.numel())
+    if ev:
+        ev[2].record()
     if host_out is not None and packed.is_cuda:
         host_out[:total].copy_(packed, non_blocking=True)
+        if ev:
+            ev[3].record()
         torch.cuda.current_stream(local.device).synchronize()
+        if ev:
+            parts.update(sizes_ms=ev[0].elapsed_time(ev[1]), all_gather_ms=ev[1].elapsed_time(ev[2]), to_host_ms=ev[2].elapsed_time(ev[3]))
         return host_out[:total].numpy(), sizes
     return packed.cpu().numpy(), sizes
