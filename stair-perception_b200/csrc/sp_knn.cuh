@@ -208,6 +208,7 @@ __device__ __forceinline__ void knn_merge128(unsigned long long *L, const unsign
 struct KnnWarp {
     unsigned long long L[KNN_CAP], B[KNN_CAP];
     float gx[KNN_CAP], gy[KNN_CAP], gz[KNN_CAP];
+    int rofs[32], rst[32];               /* fast path: exclusive candidate offset and first position of each of the 27 cell ranges */
     float pend[32][10];                  /* queries waiting for their eigen-solve: the nine sums + the neighbour count */
     float4 pq[32];                       /*                                        the query point {x, y, z, point index} */
 };
@@ -253,120 +254,188 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
     const int want = min(min(k, KNN_CAP), g.nvalid);
     const float h = g.h;
     int npend = 0;                                                      /* queries of this warp waiting for their eigen-solve (warp-uniform) */
+    float pred = 0.f;                                                   /* k-th squared distance expected for the next query (0: none yet) */
     for (int t = blockIdx.x * KNN_WARPS + wid; t < g.nvalid; t += gridDim.x * KNN_WARPS) {
         const float4 q = P[t];
         const int qi = __float_as_int(q.w);
         int a, b, c;
         sp_knn_cell(q.x, q.y, q.z, h, a, b, c);
-        for (int i = lane; i < KNN_CAP; i += 32) W.L[i] = INF;
-        __syncwarp();
-        int bn = 0;                                  /* candidates waiting in W.B (warp-uniform) */
-        unsigned long long thr = INF;                /* current want-th best */
-        bool done = false;
-        for (int shell = 0; shell <= KNN_MAX_SHELL && !done; ++shell) {
-            const int side = 2 * shell + 1, ncell = side * side * side;
-            for (int c0 = 0; c0 < ncell; c0 += 32) {
-                /* lane -> one cell of the cube; only the ring at Chebyshev distance == shell is new */
-                const int ci = c0 + lane;
-                int js = 0, je = 0, ta = 0, tb = 0, tc = 0;
-                if (ci < ncell) {
-                    const int da = ci % side - shell, db = (ci / side) % side - shell, dc = ci / (side * side) - shell;
-                    if (max(abs(da), max(abs(db), abs(dc))) == shell) {
-                        ta = a + da; tb = b + db; tc = c + dc;
-                        const unsigned hb = sp_knn_bucket(ta, tb, tc);
-                        js = bs[hb]; je = be[hb];
-                    }
-                }
-                unsigned todo = __ballot_sync(0xffffffffu, je > js);
-                while (todo) {
-                    const int src = __ffs(todo) - 1; todo &= todo - 1;
-                    const int s0 = __shfl_sync(0xffffffffu, js, src), e0 = __shfl_sync(0xffffffffu, je, src);
-                    const int xa = __shfl_sync(0xffffffffu, ta, src), xb = __shfl_sync(0xffffffffu, tb, src), xc = __shfl_sync(0xffffffffu, tc, src);
-                    for (int j0 = s0; j0 < e0; j0 += 32) {
-                        const int j = j0 + lane;
-                        bool ok = false; unsigned long long key = INF;
-                        if (j < e0) {
-                            const float4 p = P[j];
-                            int pa, pb, pc;
-                            sp_knn_cell(p.x, p.y, p.z, h, pa, pb, pc);
-                            if (pa == xa && pb == xb && pc == xc) {          /* buckets may mix cells: take this cell's points only */
-                                const float d0 = q.x - p.x, d1 = q.y - p.y, d2 = q.z - p.z;
-                                float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;      /* flann::L2_Simple */
-                                key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(p.w);
-                                ok = key < thr;
-                            }
-                        }
-                        const unsigned bm = __ballot_sync(0xffffffffu, ok);
-                        if (bm) {
-                            if (ok) W.B[bn + __popc(bm & lt)] = key;
-                            bn += __popc(bm);
-                            if (bn > KNN_CAP - 32) {
-                                for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
-                                __syncwarp();
-                                knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
-                                knn_merge128(W.L, W.B, lane);
-                                bn = 0;
-                                thr = want > 0 ? W.L[want - 1] : INF;
-                            }
-                        }
-                    }
-                }
+        /* Fast path (almost every query of a surface scan): the 27 cells around the query are looked up by 27 lanes at once and
+         * their ranges concatenated, so that the candidates fill whole warps (a cell holds ~8 points: one cell at a time used a
+         * quarter of the lanes); candidates beyond a threshold predicted from the earlier queries of this warp (the k-th distance
+         * of a uniformly sampled surface hardly varies) are dropped at once, and ONE sort of at most 128 keys replaces the
+         * sort - merge rounds.  Exactness: the filter keeps every key <= threshold, so if at least `want` pass, the `want` smallest
+         * of all candidates are among them; the shell-1 guarantee (k-th distance < h) is checked as in the general path below,
+         * which still handles everything else (first query, sparse regions, more than 128 survivors). */
+        bool fast = false;
+        if (pred > 0.f) {
+            int js = 0, je = 0;
+            if (lane < 27) {
+                const unsigned hb = sp_knn_bucket(a + lane % 3 - 1, b + (lane / 3) % 3 - 1, c + lane / 9 - 1);
+                js = bs[hb]; je = be[hb];
             }
-            if (bn) {
+            const int cc = max(je - js, 0);
+            int inc = cc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            const int C = __shfl_sync(0xffffffffu, inc, 31);
+            W.rofs[lane] = inc - cc; W.rst[lane] = js;
+            __syncwarp();
+            for (int attempt = 0; attempt < 2 && !fast; ++attempt) {
+                const unsigned long long thr0 = ((unsigned long long)__float_as_uint(pred * (attempt == 0 ? 1.3f : 2.4f)) << 32) | 0xFFFFFFFFull;
+                int bn = 0;
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    const int ci = c0 + lane;
+                    bool ok = false; unsigned long long key = INF;
+                    if (ci < C) {
+                        int kk = 0;                                      /* range of candidate ci: largest kk with rofs[kk] <= ci */
+                        if (W.rofs[kk + 16] <= ci) kk += 16;
+                        if (W.rofs[kk + 8] <= ci) kk += 8;
+                        if (W.rofs[kk + 4] <= ci) kk += 4;
+                        if (W.rofs[kk + 2] <= ci) kk += 2;
+                        if (W.rofs[kk + 1] <= ci) kk += 1;
+                        const float4 p = P[W.rst[kk] + (ci - W.rofs[kk])];
+                        int pa, pb, pc;
+                        sp_knn_cell(p.x, p.y, p.z, h, pa, pb, pc);
+                        if (pa == a + kk % 3 - 1 && pb == b + (kk / 3) % 3 - 1 && pc == c + kk / 9 - 1) {   /* buckets may mix cells */
+                            const float d0 = q.x - p.x, d1 = q.y - p.y, d2 = q.z - p.z;
+                            float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;      /* flann::L2_Simple */
+                            key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(p.w);
+                            ok = key <= thr0;
+                        }
+                    }
+                    const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                    const int at = bn + __popc(bm & lt);
+                    if (ok && at < KNN_CAP) W.B[at] = key;
+                    bn += __popc(bm);
+                }
+                if (bn > KNN_CAP) break;                                 /* too many survivors for one sort: general path */
+                if (bn < want) continue;                                 /* threshold too tight (border of a surface): once more, wider */
                 for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
                 __syncwarp();
                 knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
-                knn_merge128(W.L, W.B, lane);
-                bn = 0;
-                thr = want > 0 ? W.L[want - 1] : INF;
-            }
-            /* every point nearer than shell * h has been seen */
-            if (thr != INF && shell > 0) {
-                const float reach = (float)shell * h * 0.999f;
-                done = __uint_as_float((unsigned)(thr >> 32)) < reach * reach;
+                const float kth = __uint_as_float((unsigned)(W.B[want - 1] >> 32)), reach = h * 0.999f;
+                fast = want > 0 && kth < reach * reach;                  /* every point nearer than h has been seen */
+                if (!fast) break;
             }
         }
-        if (!done) {
-            /* isolated query: scan every point outside the cube already covered */
-            for (int j0 = 0; j0 < g.nvalid; j0 += 32) {
-                const int j = j0 + lane;
-                bool ok = false; unsigned long long key = INF;
-                if (j < g.nvalid) {
-                    const float4 p = P[j];
-                    int pa, pb, pc;
-                    sp_knn_cell(p.x, p.y, p.z, h, pa, pb, pc);
-                    if (max(abs(pa - a), max(abs(pb - b), abs(pc - c))) > KNN_MAX_SHELL) {
-                        const float d0 = q.x - p.x, d1 = q.y - p.y, d2 = q.z - p.z;
-                        float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;
-                        key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(p.w);
-                        ok = key < thr;
+        const unsigned long long *res = W.B;
+        if (!fast) {
+            res = W.L;
+            for (int i = lane; i < KNN_CAP; i += 32) W.L[i] = INF;
+            __syncwarp();
+            int bn = 0;                                  /* candidates waiting in W.B (warp-uniform) */
+            unsigned long long thr = INF;                /* current want-th best */
+            bool done = false;
+            for (int shell = 0; shell <= KNN_MAX_SHELL && !done; ++shell) {
+                const int side = 2 * shell + 1, ncell = side * side * side;
+                for (int c0 = 0; c0 < ncell; c0 += 32) {
+                    /* lane -> one cell of the cube; only the ring at Chebyshev distance == shell is new */
+                    const int ci = c0 + lane;
+                    int js = 0, je = 0, ta = 0, tb = 0, tc = 0;
+                    if (ci < ncell) {
+                        const int da = ci % side - shell, db = (ci / side) % side - shell, dc = ci / (side * side) - shell;
+                        if (max(abs(da), max(abs(db), abs(dc))) == shell) {
+                            ta = a + da; tb = b + db; tc = c + dc;
+                            const unsigned hb = sp_knn_bucket(ta, tb, tc);
+                            js = bs[hb]; je = be[hb];
+                        }
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, je > js);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1; todo &= todo - 1;
+                        const int s0 = __shfl_sync(0xffffffffu, js, src), e0 = __shfl_sync(0xffffffffu, je, src);
+                        const int xa = __shfl_sync(0xffffffffu, ta, src), xb = __shfl_sync(0xffffffffu, tb, src), xc = __shfl_sync(0xffffffffu, tc, src);
+                        for (int j0 = s0; j0 < e0; j0 += 32) {
+                            const int j = j0 + lane;
+                            bool ok = false; unsigned long long key = INF;
+                            if (j < e0) {
+                                const float4 p = P[j];
+                                int pa, pb, pc;
+                                sp_knn_cell(p.x, p.y, p.z, h, pa, pb, pc);
+                                if (pa == xa && pb == xb && pc == xc) {          /* buckets may mix cells: take this cell's points only */
+                                    const float d0 = q.x - p.x, d1 = q.y - p.y, d2 = q.z - p.z;
+                                    float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;      /* flann::L2_Simple */
+                                    key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(p.w);
+                                    ok = key < thr;
+                                }
+                            }
+                            const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                            if (bm) {
+                                if (ok) W.B[bn + __popc(bm & lt)] = key;
+                                bn += __popc(bm);
+                                if (bn > KNN_CAP - 32) {
+                                    for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
+                                    __syncwarp();
+                                    knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
+                                    knn_merge128(W.L, W.B, lane);
+                                    bn = 0;
+                                    thr = want > 0 ? W.L[want - 1] : INF;
+                                }
+                            }
+                        }
                     }
                 }
-                const unsigned bm = __ballot_sync(0xffffffffu, ok);
-                if (bm) {
-                    if (ok) W.B[bn + __popc(bm & lt)] = key;
-                    bn += __popc(bm);
-                    if (bn > KNN_CAP - 32) {
-                        for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
-                        __syncwarp();
-                        knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
-                        knn_merge128(W.L, W.B, lane);
-                        bn = 0;
-                        thr = want > 0 ? W.L[want - 1] : INF;
-                    }
+                if (bn) {
+                    for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
+                    __syncwarp();
+                    knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
+                    knn_merge128(W.L, W.B, lane);
+                    bn = 0;
+                    thr = want > 0 ? W.L[want - 1] : INF;
+                }
+                /* every point nearer than shell * h has been seen */
+                if (thr != INF && shell > 0) {
+                    const float reach = (float)shell * h * 0.999f;
+                    done = __uint_as_float((unsigned)(thr >> 32)) < reach * reach;
                 }
             }
-            if (bn) {
-                for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
-                __syncwarp();
-                knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
-                knn_merge128(W.L, W.B, lane);
-                bn = 0;
+            if (!done) {
+                /* isolated query: scan every point outside the cube already covered */
+                for (int j0 = 0; j0 < g.nvalid; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool ok = false; unsigned long long key = INF;
+                    if (j < g.nvalid) {
+                        const float4 p = P[j];
+                        int pa, pb, pc;
+                        sp_knn_cell(p.x, p.y, p.z, h, pa, pb, pc);
+                        if (max(abs(pa - a), max(abs(pb - b), abs(pc - c))) > KNN_MAX_SHELL) {
+                            const float d0 = q.x - p.x, d1 = q.y - p.y, d2 = q.z - p.z;
+                            float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;
+                            key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(p.w);
+                            ok = key < thr;
+                        }
+                    }
+                    const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                    if (bm) {
+                        if (ok) W.B[bn + __popc(bm & lt)] = key;
+                        bn += __popc(bm);
+                        if (bn > KNN_CAP - 32) {
+                            for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
+                            __syncwarp();
+                            knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
+                            knn_merge128(W.L, W.B, lane);
+                            bn = 0;
+                            thr = want > 0 ? W.L[want - 1] : INF;
+                        }
+                    }
+                }
+                if (bn) {
+                    for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
+                    __syncwarp();
+                    knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
+                    knn_merge128(W.L, W.B, lane);
+                    bn = 0;
+                }
             }
+        }
+        if (want > 0) {                                                  /* running estimate of the k-th squared distance, biased towards the small (interior) values */
+            const float kth = __uint_as_float((unsigned)(res[want - 1] >> 32));
+            if (kth < 3.0e38f) pred = pred <= 0.f ? kth : (kth < pred ? 0.5f * (pred + kth) : 0.9f * pred + 0.1f * kth);
         }
         int cnt = 0;
         for (int i = lane; i < KNN_CAP; i += 32) {
-            const unsigned long long key = W.L[i];
+            const unsigned long long key = res[i];
             const bool have = i < want && key != INF;
             if (have) {
                 const unsigned pix = (unsigned)key;
