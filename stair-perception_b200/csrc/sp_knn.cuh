@@ -175,18 +175,53 @@ __global__ void __launch_bounds__(256) k_knn_starts(SpDev d, int *bstart, int *b
 /* warp-synchronous bitonic machinery on 128 u64 keys in shared memory */
 /* ascending sort of the first n keys (n = 32, 64 or 128: a batch of waiting candidates is padded to the next of them, a second
  * batch of a query is usually half the size of the first); the keys past n must already be INF */
+/* The sort runs in REGISTERS: E = n / 32 consecutive keys per lane (key index = lane * E + r), strides below E are compare-exchanges
+ * between a lane's own registers, the others exchange with lane ^ (stride / E) by shuffle.  In shared memory the same network
+ * cost four 64-bit accesses per compare-exchange with two-way bank conflicts and made the kernel LSU-bound (l1tex 93 %). */
+template <int E>
+__device__ __forceinline__ void knn_sort_regs(unsigned long long *A, int lane)
+{
+    unsigned long long v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) v[r] = A[lane * E + r];
+#pragma unroll
+    for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < E) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & stride) == 0) {
+                        const bool asc = size < E ? ((r & size) == 0) : (((lane * E) & size) == 0);
+                        const unsigned long long x = v[r], y = v[r | stride];
+                        const bool sw = (x > y) == asc;
+                        v[r] = sw ? y : x; v[r | stride] = sw ? x : y;
+                    }
+                }
+            } else {
+                const int dl = stride / E;
+                const bool lower = (lane & dl) == 0;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const bool asc = size < E ? ((r & size) == 0) : (((lane * E) & size) == 0);
+                    const unsigned long long x = v[r];
+                    const unsigned long long y = ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(x >> 32), dl) << 32) |
+                                                 __shfl_xor_sync(0xffffffffu, (unsigned)x, dl);
+                    v[r] = ((x < y) == (lower == asc)) ? x : y;          /* the lower index keeps the minimum of an ascending pair */
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < E; ++r) A[lane * E + r] = v[r];
+    __syncwarp();
+}
 __device__ __forceinline__ void knn_sort128(unsigned long long *A, int lane, int n = 128)
 {
-    for (int size = 2; size <= n; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int q = lane; q < (n >> 1); q += 32) {
-                const int i = 2 * q - (q & (stride - 1)), j = i + stride;
-                const bool asc = (i & size) == 0;
-                const unsigned long long a = A[i], b = A[j];
-                if ((a > b) == asc) { A[i] = b; A[j] = a; }
-            }
-            __syncwarp();
-        }
+    __syncwarp();
+    if (n <= 32) knn_sort_regs<1>(A, lane);
+    else if (n <= 64) knn_sort_regs<2>(A, lane);
+    else knn_sort_regs<4>(A, lane);
 }
 __device__ __forceinline__ void knn_merge128(unsigned long long *L, const unsigned long long *B, int lane)
 {
@@ -207,7 +242,7 @@ __device__ __forceinline__ void knn_merge128(unsigned long long *L, const unsign
 
 struct KnnWarp {
     unsigned long long L[KNN_CAP], B[KNN_CAP];
-    float gx[KNN_CAP], gy[KNN_CAP], gz[KNN_CAP];
+    float4 g[KNN_CAP];                   /* the neighbours' coordinates, in list order (one 16-byte element: the three factor reads of a step hit one bank row) */
     int rofs[32], rst[32];               /* fast path: exclusive candidate offset and first position of each of the 27 cell ranges */
     float pend[32][10];                  /* queries waiting for their eigen-solve: the nine sums + the neighbour count */
     float4 pq[32];                       /*                                        the query point {x, y, z, point index} */
@@ -270,10 +305,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
         bool fast = false;
         if (pred > 0.f) {
             int js = 0, je = 0;
-            if (lane < 27) {
-                const unsigned hb = sp_knn_bucket(a + lane % 3 - 1, b + (lane / 3) % 3 - 1, c + lane / 9 - 1);
-                js = bs[hb]; je = be[hb];
-            }
+            unsigned hb = 0xffffffffu - (unsigned)lane;
+            if (lane < 27) hb = sp_knn_bucket(a + lane % 3 - 1, b + (lane / 3) % 3 - 1, c + lane / 9 - 1);
+            const unsigned same = __match_any_sync(0xffffffffu, hb);     /* two of the 27 cells in one bucket: its range is taken once */
+            if (lane < 27 && (same & lt) == 0u) { js = bs[hb]; je = be[hb]; }
             const int cc = max(je - js, 0);
             int inc = cc;
 #pragma unroll
@@ -281,8 +316,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
             const int C = __shfl_sync(0xffffffffu, inc, 31);
             W.rofs[lane] = inc - cc; W.rst[lane] = js;
             __syncwarp();
-            for (int attempt = 0; attempt < 2 && !fast; ++attempt) {
-                const unsigned long long thr0 = ((unsigned long long)__float_as_uint(pred * (attempt == 0 ? 1.3f : 2.4f)) << 32) | 0xFFFFFFFFull;
+            float tscale = 1.3f;
+            for (int attempt = 0; attempt < 3 && !fast; ++attempt) {
+                const unsigned long long thr0 = ((unsigned long long)__float_as_uint(pred * tscale) << 32) | 0xFFFFFFFFull;
                 int bn = 0;
                 for (int c0 = 0; c0 < C; c0 += 32) {
                     const int ci = c0 + lane;
@@ -297,7 +333,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
                         const float4 p = P[W.rst[kk] + (ci - W.rofs[kk])];
                         int pa, pb, pc;
                         sp_knn_cell(p.x, p.y, p.z, h, pa, pb, pc);
-                        if (pa == a + kk % 3 - 1 && pb == b + (kk / 3) % 3 - 1 && pc == c + kk / 9 - 1) {   /* buckets may mix cells */
+                        if ((unsigned)(pa - a + 1) <= 2u && (unsigned)(pb - b + 1) <= 2u && (unsigned)(pc - c + 1) <= 2u) {   /* buckets may mix cells */
                             const float d0 = q.x - p.x, d1 = q.y - p.y, d2 = q.z - p.z;
                             float dist = 0.f; dist += d0 * d0; dist += d1 * d1; dist += d2 * d2;      /* flann::L2_Simple */
                             key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(p.w);
@@ -309,8 +345,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
                     if (ok && at < KNN_CAP) W.B[at] = key;
                     bn += __popc(bm);
                 }
-                if (bn > KNN_CAP) break;                                 /* too many survivors for one sort: general path */
-                if (bn < want) continue;                                 /* threshold too tight (border of a surface): once more, wider */
+                if (bn > KNN_CAP || bn < want) {
+                    /* too many survivors for one sort, or too few (border of a surface): on a surface the count grows with the
+                     * squared radius, so aim the next threshold at 1.2 * want survivors */
+                    tscale *= 1.2f * (float)want / (float)max(bn, 4);
+                    continue;
+                }
                 for (int i = bn + lane; i < KNN_CAP; i += 32) W.B[i] = INF;
                 __syncwarp();
                 knn_sort128(W.B, lane, bn <= 32 ? 32 : (bn <= 64 ? 64 : 128));
@@ -440,7 +480,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
             if (have) {
                 const unsigned pix = (unsigned)key;
                 const float4 pw = d.xyzw[base + pix];
-                W.gx[i] = pw.x; W.gy[i] = pw.y; W.gz[i] = pw.z;
+                W.g[i] = pw;
             }
             cnt += have ? 1 : 0;
         }
@@ -449,12 +489,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 4) k_knn_normals(SpDev d, cons
         /* computeMeanAndCovarianceMatrix: nine float sums in neighbour order, lane q owns accumulator q */
         if (lane < 9) {
             /* accumulators xx xy xz yy yz zz x y z: the two factors of lane q are chosen once, outside the serial loop */
-            const float *pu = lane < 3 ? W.gx : (lane < 5 ? W.gy : (lane == 5 ? W.gz : (lane == 6 ? W.gx : (lane == 7 ? W.gy : W.gz))));
-            const float *pv = lane == 0 ? W.gx : ((lane == 1 || lane == 3) ? W.gy : W.gz);
+            const float *g0 = reinterpret_cast<const float *>(W.g);
+            const float *pu = g0 + (lane < 3 ? 0 : (lane < 5 ? 1 : (lane == 5 ? 2 : lane - 6)));
+            const float *pv = g0 + (lane == 0 ? 0 : ((lane == 1 || lane == 3) ? 1 : 2));
             const bool plain = lane >= 6;                               /* sums of x, y, z: factor 1.0f (exact) */
             float acc = 0.f;
             for (int i = 0; i < cnt; ++i) {
-                const float u = pu[i], v = plain ? 1.0f : pv[i];
+                const float u = pu[4 * i], v = plain ? 1.0f : pv[4 * i];
                 acc += u * v;
             }
             if (cnt > 0) W.pend[npend][lane] = acc;
