@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(VX_T) k_vx_scan(SpDev d, int p)
 __global__ void __launch_bounds__(VX_T, 3) k_vx_scatter(SpDev d, int p)
 {
     __shared__ __align__(16) unsigned wc[VX_NW][VX_BINS];                    /* per-warp digit counters, then the staged pairs */
-    __shared__ unsigned off[VX_BINS], wsum[VX_NW];
+    __shared__ unsigned off[VX_BINS], lst[VX_BINS], wsum[VX_NW];
     const int f = blockIdx.y, tile = blockIdx.x;
     const SpFrameGrid g = d.grid[f];
     if (p >= g.npass || tile * VX_TILE >= g.M) return;
@@ -230,12 +230,11 @@ __global__ void __launch_bounds__(VX_T, 3) k_vx_scatter(SpDev d, int p)
         for (int w = 0; w < wid; ++w) before += wsum[w];
         const unsigned ls = before + inc - tot;                              /* tile-local start of the digit */
         off[tid] = d.vth[((size_t)f * d.ntile + tile) * VX_BINS + tid] - ls; /* local position -> destination */
-#pragma unroll
-        for (int w = 0; w < VX_NW; ++w) wc[w][tid] += ls;
+        lst[tid] = ls;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < VX_E; ++k) rank[k] += wc[wid][(key[k] >> shift) & (VX_BINS - 1)];      /* tile-local sorted position */
+    for (int k = 0; k < VX_E; ++k) { const unsigned dg = (key[k] >> shift) & (VX_BINS - 1); rank[k] += wc[wid][dg] + lst[dg]; }   /* tile-local sorted position */
     __syncthreads();
     /* the pairs go through shared memory (over the counters) in digit order, so that neighbouring threads write neighbouring
      * destinations: a digit's keys of a tile are a run of ~8 consecutive words = whole 32-byte sectors, where the direct scatter
