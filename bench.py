@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=8192, help="frames of the WHOLE batch per step (config 5: 8192), sharded frame-wise across the GPUs")
     ap.add_argument("--e2e-frames", type=int, default=8192, help="frames of the whole batch per end-to-end step (pinned host input, 28.5 GB over all ranks)")
-    ap.add_argument("--max-batch", type=int, default=0, help="frames per chunk of the library (0 = 512 when a rank runs at least 4096 frames, else 256)")
+    ap.add_argument("--max-batch", type=int, default=0, help="frames per chunk of the library (0 = 512 when a rank runs at least 1024 frames, else 256)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip config 4, single-frame latency, the weak-scaling figure and the depth-image leg")
     args = ap.parse_args()
@@ -358,7 +358,7 @@ def main():
     lo, hi = shard.shard_bounds(F, rank, world)
     Fl = hi - lo
     if args.max_batch <= 0:                                   # the chunk size is a library knob, not part of the workload: 512-frame chunks
-        args.max_batch = 512 if Fl >= 4096 else 256           # measure 3 % faster than 256 when a rank has at least eight of them
+        args.max_batch = 512 if Fl >= 1024 else 256           # 2-3 % faster than 256 from two chunks per rank on (38.3 k against 37.6 k frames/s at 1024 frames)
     base = torch.from_numpy(recs.view(np.uint8).reshape(N_DISTINCT, N * 16)).to(dev)
     base_R = torch.from_numpy(Rs).to(dev)
     idx = (torch.arange(lo, hi, device=dev) % N_DISTINCT)
