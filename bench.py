@@ -375,7 +375,8 @@ def main():
     def step_device():
         # shard -> whole frames on this GPU, records stay on the device -> all-gather of the compact records -> host
         _, nb = ctx.process_frames_compact(d_clouds, d_R, device_input=True, nframes=Fl, out=cbuf)
-        last["packed"], last["sizes"] = shard.gather_compact(cbuf, nb, host_out=h_all)
+        # (every rank ends with the whole batch's records on its GPU; rank 0, the consumer, also copies them to its host)
+        last["packed"], last["sizes"] = shard.gather_compact(cbuf, nb, host_out=h_all, to_host=rank == 0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -412,17 +413,21 @@ def main():
     stage_full = ctx.stage_ms()
     clocks = sampler.stop() if rank == 0 else None
     value = F * args.steps / (ms / 1e3)
-    # what came back: every frame of the batch, in batch order, on every rank
+    # what came back: every frame of the batch, in batch order, on every rank (ranks other than 0 hold it on their GPU: copy it out now, untimed)
+    if not isinstance(last["packed"], np.ndarray):
+        last["packed"] = last["packed"].cpu().numpy()
     results = sp.expand_compact(last["packed"], F)
     assert int(results["n_planes"].min()) >= 1 and int(results["status"].max()) == 0, "unexpected empty results"
     assert np.array_equal(results[:N_DISTINCT].view(np.uint8), results[N_DISTINCT:2 * N_DISTINCT].view(np.uint8)) or F < 2 * N_DISTINCT
     # the exchange alone (sizes + compact records + copy to the host), device-timed
     gather_ms = None
+    gather_all_ms = None
     gather_parts = {}
     if world > 1:
         _, nb = ctx.process_frames_compact(d_clouds, d_R, device_input=True, nframes=Fl, out=cbuf)
-        gather_ms = timed(lambda: shard.gather_compact(cbuf, nb, host_out=h_all), 5) / 5
-        shard.gather_compact(cbuf, nb, host_out=h_all, parts=gather_parts)
+        gather_ms = timed(lambda: shard.gather_compact(cbuf, nb, host_out=h_all, to_host=rank == 0), 5) / 5
+        shard.gather_compact(cbuf, nb, host_out=h_all, parts=gather_parts, to_host=rank == 0)
+        gather_all_ms = timed(lambda: shard.gather_compact(cbuf, nb, host_out=h_all), 5) / 5
 
     # the dominant streaming kernel alone (K1K2 = ingest + levelling + masking + organised normals), CUDA events on its stream
     nb = min(256, args.max_batch, Fl)                         # 256 frames per launch: what the committed ncu captures ran
@@ -488,12 +493,14 @@ def main():
 
     def step_e2e():
         _, nbytes = ctx.process_frames_compact(h_clouds, h_R, device_input=False, nframes=Fel, out=cbuf)
-        last["packed_e"], _ = shard.gather_compact(cbuf, nbytes, host_out=h_all)
+        last["packed_e"], _ = shard.gather_compact(cbuf, nbytes, host_out=h_all, to_host=rank == 0)
 
     for _ in range(3):
         step_e2e()
     ms_e = timed(step_e2e, args.steps)
     e2e_val = Fe * args.steps / (ms_e / 1e3)
+    if not isinstance(last["packed_e"], np.ndarray):
+        last["packed_e"] = last["packed_e"].cpu().numpy()
     res_e = sp.expand_compact(last["packed_e"], Fe)
     assert np.array_equal(res_e.view(np.uint8), results[:Fe].view(np.uint8)), "host-input records differ from device-input records"
     d2h_e = int(last["packed_e"].size)
@@ -590,13 +597,14 @@ def main():
                        "l2": "inputs larger than L2 (%.1f GB resident per GPU)" % (Fl * N * 16 / 1e9),
                        "parallelism": "ONE %d-frame batch sharded frame-wise across %d GPU(s) (shard.shard_bounds), whole frames per GPU, "
                                       "all-gather of the compact plane records only (shard.gather_compact)" % (F, world),
-                       "api": "sp_process_frames_compact (records stay on the device until the exchange) + one D2H of the gathered records",
+                       "api": "sp_process_frames_compact (records stay on the device until the exchange) + all-gather on the GPUs + one D2H of the gathered records on rank 0",
                        "host_numa_binding": numa_node},
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(Fe * (N * 16 + 36)),
                     "d2h_bytes_per_step": d2h_e, "frames_per_step": Fe, "ms_per_step": ms_e / args.steps,
                     "api": "sp_process_frames_compact from pinned host clouds (H2D inside), exchange, compact records to the host (D2H inside)"},
             "gather": {"ms": gather_ms, "parts_ms_rank0": {k: round(v, 4) for k, v in gather_parts.items()}, "bytes_per_rank": [int(v) for v in last["sizes"]],
-                       "note": "sizes all-gather + padded all-gather of the compact records (NCCL, device buffers) + D2H of the whole gathered batch on EVERY rank (N copies of the same bytes share the host's PCIe / memory path), device-timed"},
+                       "ms_with_host_copy_on_every_rank": gather_all_ms,
+                       "note": "sizes all-gather + padded all-gather of the compact records (NCCL, device buffers): the whole batch's records end on every GPU, and rank 0 (the consumer) copies them to its host inside the step; ms_with_host_copy_on_every_rank = the same exchange with N copies of the same bytes to the one host, as the mid-round lines measured it; device-timed"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_ingest_normals", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

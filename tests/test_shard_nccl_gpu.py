@@ -85,6 +85,9 @@ def _worker(rank, world, port, outdir):
     buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
     _, nb = ctx.process_frames_compact(recs[lo:hi], Rs[lo:hi], out=buf)
     packed, sizes = shard.gather_compact(buf, nb)
+    # the same exchange with the gathered batch left on the GPU (what a rank that does not consume the records on its host asks for)
+    on_dev, sizes2 = shard.gather_compact(buf, nb, to_host=False)
+    assert on_dev.is_cuda and sizes2 == sizes and on_dev.cpu().numpy().tobytes() == packed.tobytes()
     np.save(os.path.join(outdir, "rank%d.npy" % rank), sp.expand_compact(packed, len(recs)).view(np.uint8))
     ctx.close()
     dist.barrier()
