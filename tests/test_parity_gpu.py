@@ -489,3 +489,29 @@ def test_batched_stair_model_equals_per_frame_model(sp, synth, samples):
     assert part.tobytes() == one[2:5].tobytes()
     assert int(one["has_stair"].sum()) >= 4 and int(one[-1]["has_stair"]) == 0 and int(res[-1]["n_planes"]) == 0
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_tapered_tail_of_a_host_batch_keeps_order_and_bits(sp, synth, monkeypatch):
+    """a host-input batch of several chunks ends in halved chunks (80, 80, 32, 8 for 200 frames of 80): record for record what
+    uniform chunks (SP_TAPER=0) and the device-input path give"""
+    import torch
+    frames = [synth.make_frame(f) for f in (31, 32, 33, 34)]
+    n = 200
+    recs = np.stack([frames[i % 4][0] for i in range(n)])
+    Rs = np.stack([frames[i % 4][1] for i in range(n)])
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=80)
+    got = ctx.process_frames(recs, Rs).copy()
+    d_c = torch.from_numpy(recs.view(np.uint8).reshape(n, -1)).cuda()
+    d_R = torch.from_numpy(Rs).cuda()
+    dev = ctx.process_frames(d_c, d_R, device_input=True, nframes=n).copy()
+    ctx.close()
+    assert int(got["n_planes"].min()) >= 8
+    assert got.tobytes() == dev.tobytes()
+    for i in range(4, n):                                                # the batch cycles four scenes
+        assert got[i].tobytes() == got[i % 4].tobytes(), i
+    monkeypatch.setenv("SP_TAPER", "0")
+    ctx = sp.Context(device=0, width=512, height=424, max_batch=80)
+    uniform = ctx.process_frames(recs, Rs).copy()
+    ctx.close()
+    assert uniform.tobytes() == got.tobytes()
