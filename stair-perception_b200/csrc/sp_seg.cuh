@@ -1040,7 +1040,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_plane_stats(SpDev d)
 __global__ void __launch_bounds__(64) k_finalize(SpDev d, int nB, int *order, int with_planes, int show_mode)
 {
     /* one CTA per frame: thread 0 replays the selection by centre.x (a few tens of planes), all threads copy the records */
-    __shared__ int s_src[SP_MAX_PLANES], s_first[SP_MAX_PLANES], s_np, s_total;
+    __shared__ int s_src[SP_MAX_PLANES], s_first[SP_MAX_PLANES], s_np;
     const int f = blockIdx.x;
     if (f >= nB) return;
     sp_frame_result &R = d.results[f];
@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(64) k_finalize(SpDev d, int nB, int *order, in
             order[f * SP_MAX_PLANES + np] = m | ((in_h ? 0 : 1) << 16);
             ++np;
         }
-        s_np = np; s_total = first;
+        s_np = np;
         R.n_planes = np; R.n_plane_points = first;
     }
     __syncthreads();
