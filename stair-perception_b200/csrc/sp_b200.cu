@@ -129,7 +129,11 @@ struct sp_ctx {
     SpKnnGrid *knn_grid = nullptr;
     float4 *knn_pts = nullptr;
     /* depth-image ingest (sp_process_depth_frames): staging buffers, allocated on first use */
-    void *d_depth[2] = { nullptr, nullptr }; unsigned char *d_color[2] = { nullptr, nullptr };
+    /* depth-image entry point: a ring of four input buffers (depth, colour, the records k_depth_to_records makes of them, rotations), so
+     * that the copies run two chunks ahead of the two lanes (with two buffers a lane waited for its input while the other computed) */
+    void *d_depth[4] = { nullptr, nullptr, nullptr, nullptr }; unsigned char *d_color[4] = { nullptr, nullptr, nullptr, nullptr };
+    float4 *d_din[4] = { nullptr, nullptr, nullptr, nullptr }; float *d_dR[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t evd_in[4] = { nullptr, nullptr, nullptr, nullptr }, evd_done[4] = { nullptr, nullptr, nullptr, nullptr };
     float *d_maps = nullptr;                 /* colmap[W] then rowmap[H] */
     /* K1K2 variant: 0 = tile kernel with plain loads (k_ingest_normals), 1 = the row-marching TMA kernel (sp_strip.cuh),
      * 2 = tile kernel fed by one TMA tensor copy per tile (k_ingest_normals_tma).  SP_K1 = tile | strip | tma picks one. */
@@ -505,6 +509,7 @@ void sp_destroy(sp_ctx *ctx)
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     for (int i = 0; i <= STG_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
+    for (int i = 0; i < 4; ++i) { if (ctx->evd_in[i]) cudaEventDestroy(ctx->evd_in[i]); if (ctx->evd_done[i]) cudaEventDestroy(ctx->evd_done[i]); }
     for (cudaEvent_t e : ctx->tev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) if (ctx->ev_res[i]) cudaEventDestroy(ctx->ev_res[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -754,12 +759,22 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
     const size_t N = ctx->N, B = ctx->B, dsz = depth_type == 0 ? 4 : 2;
     if (!ctx->d_maps) {
         cudaError_t e;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             void *q = nullptr;
             if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (depth staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
             ctx->allocs.push_back(q); ctx->d_depth[i] = q;
             if ((e = cudaMalloc(&q, B * N * 4)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (colour staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
             ctx->allocs.push_back(q); ctx->d_color[i] = (unsigned char *)q;
+            if (i < 2 && ctx->d_in[i] && ctx->d_R[i]) { ctx->d_din[i] = ctx->d_in[i]; ctx->d_dR[i] = ctx->d_R[i]; }
+            else {
+                if ((e = cudaMalloc(&q, B * N * 16)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (record staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+                ctx->allocs.push_back(q); ctx->d_din[i] = (float4 *)q;
+                if ((e = cudaMalloc(&q, B * 9 * sizeof(float))) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (rotation staging): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
+                ctx->allocs.push_back(q); ctx->d_dR[i] = (float *)q;
+            }
+            if ((e = cudaEventCreateWithFlags(&ctx->evd_in[i], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->evd_done[i], cudaEventDisableTiming)) != cudaSuccess) {
+                ERR(ctx) = std::string("cudaEventCreate: ") + cudaGetErrorString(e); return SP_ERR_CUDA;
+            }
         }
         if ((e = dalloc(ctx, &ctx->d_maps, (size_t)ctx->W + ctx->H)) != cudaSuccess) { ERR(ctx) = std::string("cudaMalloc (maps): ") + cudaGetErrorString(e); return SP_ERR_CUDA; }
     }
@@ -776,11 +791,11 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
     const int nchunks = (int)cstart.size();
     auto issue_copy = [&](int ci, int b) -> int {
         const int f0 = cstart[ci], nB = csize[ci];
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->evd_done[b], 0));
         CK(cudaMemcpyAsync(ctx->d_depth[b], (const uint8_t *)depth + N * dsz * f0, N * dsz * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
         if (bgrx) CK(cudaMemcpyAsync(ctx->d_color[b], bgrx + N * 4 * f0, N * 4 * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
-        if (R9) CK(cudaMemcpyAsync(ctx->d_R[b], R9 + 9 * (size_t)f0, sizeof(float) * 9 * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CK(cudaEventRecord(ctx->ev_in[b], ctx->copy_stream));
+        if (R9) CK(cudaMemcpyAsync(ctx->d_dR[b], R9 + 9 * (size_t)f0, sizeof(float) * 9 * nB, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->evd_in[b], ctx->copy_stream));
         return SP_OK;
     };
     /* two lanes like sp_process_frames: chunks alternate between this context and its twin */
@@ -797,7 +812,7 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         }
         return SP_OK;
     };
-    int buf = 0;
+    const int NBUF = 4;
     auto settle = [&](int rc) -> int {                       /* as in process_impl: no copy stays in flight after an error */
         if (rc != SP_OK) {
             cudaStreamSynchronize(ctx->copy_stream);
@@ -809,25 +824,24 @@ int sp_process_depth_frames(sp_ctx *ctx, const void *depth, int depth_type, cons
         return rc;
     };
     auto run_batch = [&]() -> int {
-    if (nchunks > 0) { const int rc = issue_copy(0, 0); if (rc) return rc; }
+    for (int ci = 0; ci < std::min(nchunks, NBUF - 1); ++ci) { const int rc = issue_copy(ci, ci); if (rc) return rc; }
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int f0 = cstart[ci], nB = csize[ci];
+        const int f0 = cstart[ci], nB = csize[ci], buf = ci % NBUF;
         sp_ctx *L = lanes[ci % nl];
         const int hb = (ci / nl) & 1;
-        CK(cudaStreamWaitEvent(L->stream, ctx->ev_in[buf], 0));
-        if (ci + 1 < nchunks) { const int rc = issue_copy(ci + 1, buf ^ 1); if (rc) return rc; }
+        CK(cudaStreamWaitEvent(L->stream, ctx->evd_in[buf], 0));
+        if (ci + NBUF - 1 < nchunks) { const int rc = issue_copy(ci + NBUF - 1, (ci + NBUF - 1) % NBUF); if (rc) return rc; }   /* the buffer chunk ci - 1 used */
         k_depth_to_records<<<dim3(std::min(ctx->d.nblk, 148), nB), 256, 0, L->stream>>>(ctx->d_depth[buf], depth_type, bgrx ? ctx->d_color[buf] : nullptr,
-                                                                                           ctx->d_maps, ctx->d_maps + ctx->W, ctx->W, ctx->H, mirror ? 1 : 0, ctx->d_in[buf]);
+                                                                                           ctx->d_maps, ctx->d_maps + ctx->W, ctx->W, ctx->H, mirror ? 1 : 0, ctx->d_din[buf]);
         L->launches += 1;
         CK(cudaMemsetAsync(L->d.results, 0, sizeof(sp_frame_result) * nB, L->stream));
-        const int rc = run_chunk(L, ctx->d_in[buf], R9 ? ctx->d_R[buf] : nullptr, nB, show_mode, -1);
+        const int rc = run_chunk(L, ctx->d_din[buf], R9 ? ctx->d_dR[buf] : nullptr, nB, show_mode, -1);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_done[buf], L->stream));
+        CK(cudaEventRecord(ctx->evd_done[buf], L->stream));
         CK(cudaMemcpyAsync(L->h_results + (size_t)hb * ctx->B, L->d.results, sizeof(sp_frame_result) * nB, cudaMemcpyDeviceToHost, L->stream));
         CK(cudaEventRecord(L->ev_res[hb], L->stream));
         pend.push_back({ L->ev_res[hb], L->h_results + (size_t)hb * ctx->B, f0, nB });
         { const int rd = drain((size_t)nl); if (rd) return rd; }
-        buf ^= 1;
     }
     { const int rd = drain(0); if (rd) return rd; }
     if (nchunks > 0) {
