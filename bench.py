@@ -113,28 +113,44 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """call at the start of the timed region (the sampler is started earlier, during the warm-up, so that it is already
+        delivering rows: nvidia-smi needs a few hundred ms to print its first one and an 8-GPU step lasts 27 ms)"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t1 = time.perf_counter()
+        t0 = getattr(self, "t0", 0.0)
+        deadline = t1 + 1.5
+        while time.perf_counter() < deadline and not any(t >= t1 for t, _ in self.rows):
+            time.sleep(0.02)                                   # one row after the region closes it from the right
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        good = [(t, r) for t, r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        inside = [r for t, r in good if t0 <= t <= t1]
+        where = "inside the timed region"
+        if not inside:                                         # region shorter than the sampling period: the rows that bracket it
+            before = [r for t, r in good if t < t0][-1:]
+            after = [r for t, r in good if t > t1][:1]
+            inside = before + after
+            where = "the rows bracketing the timed region (it is shorter than the 100 ms sampling period); the GPU ran the same steps (warm-up) when the earlier one was taken"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 8:
-                for k, nm in enumerate(names):
-                    if r[4 + k].lower().startswith("active"):
-                        reasons.add(nm)
+        for r in inside:
+            for k, nm in enumerate(names):
+                if r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampled": where}
 
 
 def _one_frame(i):
@@ -402,11 +418,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(3, args.warmup)):
-        step_device()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                        # already running through the warm-up: see ClockSampler.mark
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sampler.mark()
     l0 = ctx.launch_count()
     ms = timed(step_device, args.steps)
     launches = ctx.launch_count() - l0
